@@ -1,0 +1,356 @@
+"""ctypes wrapper over oracle/libgranne_oracle.so — the CPU restatement of granne's search path.
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+`--impl reference` legs.  The product package (granne_b200/) never imports this module.
+
+The class surface mirrors the reference's Python module (py/src/lib.rs:149-344 `Granne`, :346-579
+`GranneBuilder`) closely enough that the parity tests read like the reference's own tests.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libgranne_oracle.so")
+
+ANGULAR, ANGULAR_INT, EMBEDDINGS = 0, 1, 2
+_KINDS = {"angular": ANGULAR, "angular_int": ANGULAR_INT, "embeddings": EMBEDDINGS}
+UNUSED = 0xFFFFFFFF
+
+
+def build_lib(force=False):
+    """Compile the oracle with oracle/Makefile (g++ only; no reference sources are compiled)."""
+    src = os.path.join(_HERE, "granne_oracle.cpp")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    build_lib()
+    L = C.CDLL(_LIB_PATH)
+    vp, u64, i64, f32, i32 = C.c_void_p, C.c_uint64, C.c_int64, C.c_float, C.c_int
+    sig = {
+        "orc_last_error": (C.c_char_p, []),
+        "orc_num_elements_in_layer": (u64, [u64, f32, u64]),
+        "orc_dot_f32": (f32, [vp, vp, u64]),
+        "orc_normalize_f32": (None, [vp, u64]),
+        "orc_sum_into_f32": (None, [vp, vp, u64]),
+        "orc_dist_f32": (f32, [vp, vp, u64]),
+        "orc_dist_i8": (f32, [vp, vp, u64]),
+        "orc_quantize_i8": (None, [vp, u64, vp]),
+        "orc_dot_i8": (None, [vp, vp, u64, vp]),
+        "orc_read_uint": (u64, [vp, i32]),
+        "orc_write_uint": (None, [vp, u64, i32]),
+        "orc_set_encode": (u64, [vp, u64, vp, u64]),
+        "orc_set_decode": (u64, [vp, u64, vp, u64]),
+        "orc_delta_encode": (None, [vp, u64]),
+        "orc_elements_new": (vp, [i32, u64]),
+        "orc_elements_free": (None, [vp]),
+        "orc_elements_len": (u64, [vp]),
+        "orc_elements_dim": (u64, [vp]),
+        "orc_elements_push_f32": (None, [vp, vp, u64, i32]),
+        "orc_elements_push_i8": (None, [vp, vp, u64]),
+        "orc_sum_push_embeddings": (None, [vp, vp, u64]),
+        "orc_sum_push_element": (None, [vp, vp, u64]),
+        "orc_elements_data": (vp, [vp]),
+        "orc_elements_get": (None, [vp, u64, vp]),
+        "orc_elements_dist_to": (f32, [vp, u64, vp, i32]),
+        "orc_elements_serialize": (u64, [vp, i32, vp, u64]),
+        "orc_elements_from_bytes": (vp, [i32, vp, u64, vp, u64]),
+        "orc_index_free": (None, [vp]),
+        "orc_index_from_bytes": (vp, [vp, u64]),
+        "orc_build": (vp, [vp, u64, u64, f32, i32, i64, u64, i32]),
+        "orc_index_serialize": (u64, [vp, vp, u64]),
+        "orc_index_to_fixed": (vp, [vp]),
+        "orc_index_len": (u64, [vp]),
+        "orc_index_num_layers": (u64, [vp]),
+        "orc_index_layer_len": (u64, [vp, u64]),
+        "orc_index_get_neighbors": (u64, [vp, u64, u64, vp, u64]),
+        "orc_search_batch": (i32, [vp, vp, vp, vp, u64, i32, u64, u64, vp, vp, vp, vp, i32]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+# ---- KAT helpers -------------------------------------------------------------------------------------------------
+def num_elements_in_layer(total, multiplier, layer):
+    return int(lib().orc_num_elements_in_layer(total, multiplier, layer))
+
+
+def dot_product_f32(x, y):
+    x, y = _f32(x), _f32(y)
+    return float(np.float32(lib().orc_dot_f32(_ptr(x), _ptr(y), x.size)))
+
+
+def normalize_f32(x):
+    x = _f32(x).copy()
+    lib().orc_normalize_f32(_ptr(x), x.size)
+    return x
+
+
+def sum_into_f32(x, y):
+    x, y = _f32(x).copy(), _f32(y)
+    lib().orc_sum_into_f32(_ptr(x), _ptr(y), x.size)
+    return x
+
+
+def dist_f32(x, y):
+    x, y = _f32(x), _f32(y)
+    return np.float32(lib().orc_dist_f32(_ptr(x), _ptr(y), x.size))
+
+
+def quantize_i8(x):
+    x = _f32(x)
+    out = np.empty(x.size, dtype=np.int8)
+    lib().orc_quantize_i8(_ptr(x), x.size, _ptr(out))
+    return out
+
+
+def dist_i8(x, y):
+    x = np.ascontiguousarray(x, dtype=np.int8)
+    y = np.ascontiguousarray(y, dtype=np.int8)
+    return np.float32(lib().orc_dist_i8(_ptr(x), _ptr(y), x.size))
+
+
+def dot_i8(x, y):
+    x = np.ascontiguousarray(x, dtype=np.int8)
+    y = np.ascontiguousarray(y, dtype=np.int8)
+    out = np.zeros(3, dtype=np.int32)
+    lib().orc_dot_i8(_ptr(x), _ptr(y), x.size, _ptr(out))
+    return tuple(int(v) for v in out)
+
+
+def read_uint(b, nbytes):
+    a = np.frombuffer(bytes(b), dtype=np.uint8)
+    return int(lib().orc_read_uint(_ptr(a), nbytes))
+
+
+def write_uint(v, nbytes):
+    a = np.zeros(nbytes, dtype=np.uint8)
+    lib().orc_write_uint(_ptr(a), v, nbytes)
+    return a.tobytes()
+
+
+def set_encode(sorted_ids):
+    ids = np.ascontiguousarray(sorted_ids, dtype=np.uint32)
+    out = np.zeros(8 + 5 * max(4, ids.size), dtype=np.uint8)
+    n = lib().orc_set_encode(_ptr(ids), ids.size, _ptr(out), out.size)
+    return out[:n].tobytes()
+
+
+def set_decode(enc):
+    a = np.frombuffer(bytes(enc), dtype=np.uint8)
+    out = np.zeros(260, dtype=np.uint32)
+    n = lib().orc_set_decode(_ptr(a), a.size, _ptr(out), out.size)
+    return out[:n].tolist()
+
+
+def delta_encode(ids):
+    a = np.ascontiguousarray(ids, dtype=np.uint32).copy()
+    lib().orc_delta_encode(_ptr(a), a.size)
+    return a.tolist()
+
+
+# ---- element containers ------------------------------------------------------------------------------------------
+class Elements:
+    """angular::Vectors / angular_int::Vectors / embeddings::SumEmbeddings (src/elements/)."""
+
+    def __init__(self, kind, dim, _handle=None):
+        self.kind = _KINDS[kind] if isinstance(kind, str) else kind
+        self._h = _handle if _handle is not None else lib().orc_elements_new(self.kind, dim)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_elements_free(self._h)
+            self._h = None
+
+    @classmethod
+    def angular(cls, raw, as_is=False):
+        raw = _f32(raw)
+        e = cls(ANGULAR, raw.shape[1])
+        lib().orc_elements_push_f32(e._h, _ptr(raw), raw.shape[0], int(as_is))
+        return e
+
+    @classmethod
+    def angular_int(cls, raw):
+        """raw f32 rows are quantised (angular_int.rs:28-45); int8 rows are stored as is."""
+        raw = np.asarray(raw)
+        e = cls(ANGULAR_INT, raw.shape[1])
+        if raw.dtype == np.int8:
+            raw = np.ascontiguousarray(raw)
+            lib().orc_elements_push_i8(e._h, _ptr(raw), raw.shape[0])
+        else:
+            raw = _f32(raw)
+            lib().orc_elements_push_f32(e._h, _ptr(raw), raw.shape[0], 0)
+        return e
+
+    @classmethod
+    def sum_embeddings(cls, embeddings, elements):
+        embeddings = _f32(embeddings)
+        e = cls(EMBEDDINGS, embeddings.shape[1])
+        lib().orc_sum_push_embeddings(e._h, _ptr(embeddings), embeddings.shape[0])
+        for el in elements:
+            ids = np.ascontiguousarray(el, dtype=np.uint32)
+            lib().orc_sum_push_element(e._h, _ptr(ids), ids.size)
+        return e
+
+    @classmethod
+    def from_bytes(cls, kind, elements_bytes, embeddings_bytes=None):
+        kind = _KINDS[kind] if isinstance(kind, str) else kind
+        a = np.frombuffer(elements_bytes, dtype=np.uint8)
+        if embeddings_bytes is not None:
+            b = np.frombuffer(embeddings_bytes, dtype=np.uint8)
+            h = lib().orc_elements_from_bytes(kind, _ptr(a), a.size, _ptr(b), b.size)
+        else:
+            h = lib().orc_elements_from_bytes(kind, _ptr(a), a.size, None, 0)
+        if not h:
+            raise ValueError(lib().orc_last_error().decode())
+        return cls(kind, 0, _handle=h)
+
+    def __len__(self):
+        return int(lib().orc_elements_len(self._h))
+
+    @property
+    def dim(self):
+        return int(lib().orc_elements_dim(self._h))
+
+    def get(self, idx):
+        out = np.empty(self.dim, dtype=np.int8 if self.kind == ANGULAR_INT else np.float32)
+        lib().orc_elements_get(self._h, idx, _ptr(out))
+        return out
+
+    def rows(self):
+        """The stored rows (f32/i8 vectors, or the embedding table for SumEmbeddings) as a numpy copy."""
+        n = len(self)
+        p = lib().orc_elements_data(self._h)
+        if self.kind == ANGULAR_INT:
+            return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_int8)), shape=(n, self.dim)).copy()
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(n, self.dim)).copy()
+
+    def dist_to_element(self, idx, raw_query, already_element=False):
+        q = _f32(raw_query)
+        return np.float32(lib().orc_elements_dist_to(self._h, idx, _ptr(q), int(already_element)))
+
+    def to_bytes(self, which=0):
+        """io::Writeable::write.  which=1: the SumEmbeddings embeddings table."""
+        n = lib().orc_elements_serialize(self._h, which, None, 0)
+        out = np.empty(n, dtype=np.uint8)
+        lib().orc_elements_serialize(self._h, which, _ptr(out), n)
+        return out.tobytes()
+
+
+# ---- index -------------------------------------------------------------------------------------------------------
+class Granne:
+    """granne::Granne (src/index/mod.rs:38-160) over the oracle."""
+
+    def __init__(self, handle, elements):
+        self._h = handle
+        self.elements = elements
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_index_free(self._h)
+            self._h = None
+
+    @classmethod
+    def from_bytes(cls, index_bytes, elements):
+        a = np.frombuffer(index_bytes, dtype=np.uint8)
+        h = lib().orc_index_from_bytes(_ptr(a), a.size)
+        if not h:
+            raise ValueError(lib().orc_last_error().decode())
+        return cls(h, elements)
+
+    def to_fixed(self):
+        """Pre-decoded adjacency (the 'strong' CPU baseline variant)."""
+        return Granne(lib().orc_index_to_fixed(self._h), self.elements)
+
+    def __len__(self):
+        return int(lib().orc_index_len(self._h))
+
+    def num_layers(self):
+        return int(lib().orc_index_num_layers(self._h))
+
+    def layer_len(self, layer):
+        return int(lib().orc_index_layer_len(self._h, layer))
+
+    def get_neighbors(self, idx, layer=None):
+        if layer is None:
+            layer = self.num_layers() - 1
+        out = np.zeros(256, dtype=np.uint32)
+        n = lib().orc_index_get_neighbors(self._h, idx, layer, _ptr(out), out.size)
+        return out[:n].tolist()
+
+    def to_bytes(self):
+        """Index::write_index (src/index/io.rs:11-70)."""
+        n = lib().orc_index_serialize(self._h, None, 0)
+        out = np.empty(n, dtype=np.uint8)
+        lib().orc_index_serialize(self._h, _ptr(out), n)
+        return out.tobytes()
+
+    def search_batch(self, queries, max_search=200, num_neighbors=10, already_element=False, threads=1,
+                     with_stats=False):
+        """Runs Granne::search for every row of `queries` (raw f32; normalised/quantised like the reference's
+        Python binding does, py/src/variants/index.rs:15-16,32-33) — or, with already_element, rows that are
+        already elements (normalised f32 / int8)."""
+        L = lib()
+        q = np.asarray(queries)
+        qi8 = None
+        if q.dtype == np.int8:
+            qi8 = np.ascontiguousarray(q)
+            qf = np.zeros((q.shape[0], q.shape[1]), dtype=np.float32)
+            already_element = True
+        else:
+            qf = _f32(q)
+        nq = qf.shape[0]
+        ids = np.empty((nq, num_neighbors), dtype=np.uint32)
+        dists = np.empty((nq, num_neighbors), dtype=np.float32)
+        counts = np.empty(nq, dtype=np.uint32)
+        stats = np.zeros((nq, 3), dtype=np.uint64)
+        rc = L.orc_search_batch(self._h, self.elements._h, _ptr(qf), _ptr(qi8) if qi8 is not None else None, nq,
+                                int(already_element), max_search, num_neighbors, _ptr(ids), _ptr(dists),
+                                _ptr(counts), _ptr(stats), threads)
+        if rc != 0:
+            raise ValueError(L.orc_last_error().decode())
+        if with_stats:
+            return ids, dists, counts, stats
+        return ids, dists, counts
+
+    def search(self, element, max_search=200, num_elements=10):
+        ids, dists, counts = self.search_batch(np.asarray(element)[None, :], max_search, num_elements)
+        return [(int(ids[0, i]), float(dists[0, i])) for i in range(counts[0])]
+
+
+class GranneBuilder:
+    """granne::GranneBuilder (src/index/mod.rs:295-531) — fixture generator."""
+
+    def __init__(self, elements, num_neighbors=30, max_search=200, layer_multiplier=15.0, reinsert_elements=True,
+                 expected_num_elements=None):
+        self.elements = elements
+        self.cfg = (num_neighbors, max_search, layer_multiplier, reinsert_elements,
+                    -1 if expected_num_elements is None else expected_num_elements)
+
+    def build(self, num_elements=0, threads=1):
+        m, ef, mult, re, exp = self.cfg
+        h = lib().orc_build(self.elements._h, m, ef, mult, int(re), exp, num_elements, threads)
+        return Granne(h, self.elements)
