@@ -1,0 +1,278 @@
+"""ctypes binding over include/granne_b200.h."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "libgranne_b200.so")
+
+ANGULAR, ANGULAR_INT, EMBEDDINGS = 0, 1, 2
+QUERY_RAW_F32, QUERY_ELEMENT = 0, 1
+_ELEMENT_TYPES = {"angular": ANGULAR, "angular_int": ANGULAR_INT, "embeddings": EMBEDDINGS}
+STATS_PER_QUERY = 4
+DEFAULT_MAX_SEARCH = 200   # py/src/lib.rs:14
+DEFAULT_NUM_ELEMENTS = 10  # py/src/lib.rs:15
+
+
+class GranneError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("granne_b200 error %d: %s" % (code, message))
+        self.code = code
+
+
+def library_path():
+    return _LIB
+
+
+_lib = None
+
+
+def load_library():
+    """Loads libgranne_b200.so; raises if it has not been built (python -m granne_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB):
+        raise ImportError("granne_b200: %s is missing — build it with `python -m granne_b200.build` "
+                          "(there is no CPU fallback)" % _LIB)
+    L = C.CDLL(_LIB)
+    vp, sz, u64, u32, i32 = C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint32, C.c_int
+    sig = {
+        "granne_b200_abi_version": (i32, []),
+        "granne_b200_last_error": (C.c_char_p, []),
+        "granne_b200_open": (i32, [vp, sz, i32, vp, sz, vp, sz, i32, C.POINTER(vp)]),
+        "granne_b200_open_files": (i32, [C.c_char_p, i32, C.c_char_p, C.c_char_p, i32, C.POINTER(vp)]),
+        "granne_b200_close": (None, [vp]),
+        "granne_b200_len": (u64, [vp]),
+        "granne_b200_num_layers": (u64, [vp]),
+        "granne_b200_layer_len": (u64, [vp, u64]),
+        "granne_b200_get_neighbors": (i32, [vp, u64, u64, vp, sz, C.POINTER(sz)]),
+        "granne_b200_num_elements": (u64, [vp]),
+        "granne_b200_dim": (u64, [vp]),
+        "granne_b200_element_kind": (i32, [vp]),
+        "granne_b200_get_element": (i32, [vp, u64, vp]),
+        "granne_b200_search_batch": (i32, [vp, vp, sz, i32, u32, u32, vp, vp, vp, vp]),
+        "granne_b200_search_batch_device": (i32, [vp, vp, sz, i32, u32, u32, vp, vp, vp, vp, vp]),
+        "granne_b200_stream_status": (i32, [vp]),
+        "granne_b200_merge_topk_device": (i32, [i32, vp, vp, vp, sz, sz, u32, vp, vp, vp]),
+        "granne_b200_inspect_index": (i32, [vp, sz, vp, vp, vp, vp, sz]),
+        "granne_b200_decode_layer": (i32, [vp, sz, u64, vp, sz]),
+        "granne_b200_launch_count": (u64, [vp]),
+        "granne_b200_device_bytes": (u64, [vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise GranneError(rc, load_library().granne_b200_last_error().decode("utf-8", "replace"))
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _kind(element_type):
+    if isinstance(element_type, str):
+        try:
+            return _ELEMENT_TYPES[element_type.lower()]
+        except KeyError:
+            raise ValueError("Invalid element type")  # py/src/lib.rs:208
+    return int(element_type)
+
+
+class Granne:
+    """granne.Granne (py/src/lib.rs:149-344) on the GPU.
+
+    Granne(index_path, element_type, elements_path, embeddings_path=None, words_path=None, device=0)
+    element_type: "angular" | "angular_int" | "embeddings".  `words_path` is accepted for signature compatibility;
+    string queries (word lookup, py/src/variants/mod.rs:9-78) are outside the search path — pass vectors.
+    """
+
+    def __init__(self, index_path, element_type, elements_path, embeddings_path=None, words_path=None, device=0):
+        L = load_library()
+        h = C.c_void_p()
+        kind = _kind(element_type)
+        if kind == EMBEDDINGS and embeddings_path is None:
+            raise ValueError("embeddings_path required for this element type!")
+        _check(L.granne_b200_open_files(os.fsencode(index_path), kind, os.fsencode(elements_path),
+                                        os.fsencode(embeddings_path) if embeddings_path else None, device,
+                                        C.byref(h)))
+        self._h = h
+        self.device = device
+
+    @classmethod
+    def from_bytes(cls, index_bytes, element_type, elements_bytes, embeddings_bytes=None, device=0):
+        """Granne::from_bytes (src/index/mod.rs:108-113) + Vectors::from_bytes / SumEmbeddings::from_bytes."""
+        L = load_library()
+        self = cls.__new__(cls)
+        h = C.c_void_p()
+        ib = np.frombuffer(index_bytes, dtype=np.uint8)
+        eb = np.frombuffer(elements_bytes, dtype=np.uint8)
+        mb = np.frombuffer(embeddings_bytes, dtype=np.uint8) if embeddings_bytes is not None else None
+        _check(L.granne_b200_open(_ptr(ib), ib.size, _kind(element_type), _ptr(eb), eb.size,
+                                  _ptr(mb) if mb is not None else None, mb.size if mb is not None else 0, device,
+                                  C.byref(h)))
+        self._h = h
+        self.device = device
+        return self
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load_library().granne_b200_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- Index trait ----
+    def __len__(self):
+        return int(load_library().granne_b200_len(self._h))
+
+    def num_layers(self):
+        return int(load_library().granne_b200_num_layers(self._h))
+
+    def layer_len(self, layer):
+        return int(load_library().granne_b200_layer_len(self._h, layer))
+
+    def get_neighbors(self, idx, layer=None):
+        if layer is None:
+            layer = self.num_layers() - 1  # py/src/lib.rs:268-276
+        out = np.empty(256, dtype=np.uint32)
+        n = C.c_size_t()
+        _check(load_library().granne_b200_get_neighbors(self._h, idx, layer, _ptr(out), out.size, C.byref(n)))
+        return out[:n.value].tolist()
+
+    # ---- ElementContainer ----
+    @property
+    def dim(self):
+        return int(load_library().granne_b200_dim(self._h))
+
+    @property
+    def element_kind(self):
+        return int(load_library().granne_b200_element_kind(self._h))
+
+    def num_elements(self):
+        return int(load_library().granne_b200_num_elements(self._h))
+
+    def get_element(self, idx):
+        out = np.empty(self.dim, dtype=np.int8 if self.element_kind == ANGULAR_INT else np.float32)
+        _check(load_library().granne_b200_get_element(self._h, idx, _ptr(out)))
+        return out
+
+    # ---- search ----
+    def search_batch(self, queries, max_search=DEFAULT_MAX_SEARCH, num_elements=DEFAULT_NUM_ELEMENTS,
+                     already_element=False, with_stats=False):
+        """nq independent Granne::search calls (src/index/mod.rs:140-150) in one launch; host buffers in and out.
+
+        queries: (nq, dim) float32 raw vectors (normalised / quantised by the library like the reference's Python
+        binding), or with already_element=True rows that already are elements (normalised f32; int8 for
+        angular_int).  Returns (ids uint32 [nq,k] padded 0xFFFFFFFF, dists float32 [nq,k] padded +inf, counts)."""
+        q = np.asarray(queries)
+        fmt = QUERY_ELEMENT if already_element else QUERY_RAW_F32
+        if q.dtype == np.int8:
+            if self.element_kind != ANGULAR_INT:
+                raise ValueError("int8 queries need an angular_int index")
+            fmt = QUERY_ELEMENT
+            q = np.ascontiguousarray(q)
+        else:
+            q = np.ascontiguousarray(q, dtype=np.float32)
+            if fmt == QUERY_ELEMENT and self.element_kind == ANGULAR_INT:
+                raise ValueError("angular_int elements are int8")
+        if q.ndim != 2 or q.shape[1] != self.dim:
+            raise ValueError("queries must have shape (nq, %d)" % self.dim)
+        nq, k = q.shape[0], int(num_elements)
+        ids = np.empty((nq, k), dtype=np.uint32)
+        dists = np.empty((nq, k), dtype=np.float32)
+        counts = np.empty(nq, dtype=np.uint32)
+        stats = np.zeros((nq, STATS_PER_QUERY), dtype=np.uint64) if with_stats else None
+        _check(load_library().granne_b200_search_batch(self._h, _ptr(q), nq, fmt, int(max_search), k, _ptr(ids),
+                                                       _ptr(dists), _ptr(counts),
+                                                       _ptr(stats) if with_stats else None))
+        if with_stats:
+            return ids, dists, counts, stats
+        return ids, dists, counts
+
+    def search(self, element, max_search=DEFAULT_MAX_SEARCH, num_elements=DEFAULT_NUM_ELEMENTS):
+        """Granne.search(element, max_search=200, num_elements=10) -> [(id, distance)] (py/src/lib.rs:227-233)."""
+        ids, dists, counts = self.search_batch(np.asarray(element)[None, :], max_search, num_elements)
+        return [(int(ids[0, i]), float(dists[0, i])) for i in range(int(counts[0]))]
+
+    def search_batch_device(self, queries, max_search=DEFAULT_MAX_SEARCH, num_elements=DEFAULT_NUM_ELEMENTS,
+                            already_element=False, out=None, stats=None, stream=None):
+        """Device-resident variant: `queries` is a CUDA torch tensor on this index's device; returns CUDA tensors
+        (ids int32 view of u32 bits, dists float32, counts int32).  Asynchronous on the current torch stream."""
+        import torch
+
+        q = queries
+        fmt = QUERY_ELEMENT if already_element or q.dtype == torch.int8 else QUERY_RAW_F32
+        nq, k = q.shape[0], int(num_elements)
+        if out is None:
+            dev = q.device
+            out = (torch.empty((nq, k), dtype=torch.int32, device=dev),
+                   torch.empty((nq, k), dtype=torch.float32, device=dev),
+                   torch.empty((nq,), dtype=torch.int32, device=dev))
+        ids, dists, counts = out
+        s = stream if stream is not None else torch.cuda.current_stream(q.device).cuda_stream
+        _check(load_library().granne_b200_search_batch_device(
+            self._h, C.c_void_p(q.data_ptr()), nq, fmt, int(max_search), k, C.c_void_p(ids.data_ptr()),
+            C.c_void_p(dists.data_ptr()), C.c_void_p(counts.data_ptr()),
+            C.c_void_p(stats.data_ptr()) if stats is not None else None, C.c_void_p(s)))
+        return ids, dists, counts
+
+    def stream_status(self):
+        _check(load_library().granne_b200_stream_status(self._h))
+
+    def launch_count(self):
+        return int(load_library().granne_b200_launch_count(self._h))
+
+    def device_bytes(self):
+        return int(load_library().granne_b200_device_bytes(self._h))
+
+
+def inspect_index(index_bytes):
+    """Host-only: [(layer_len, max_degree, row_width)] per layer of a granne index image."""
+    L = load_library()
+    ib = np.frombuffer(index_bytes, dtype=np.uint8)
+    nl = C.c_uint64()
+    lens = np.zeros(64, dtype=np.uint64)
+    degs = np.zeros(64, dtype=np.uint32)
+    widths = np.zeros(64, dtype=np.uint32)
+    _check(L.granne_b200_inspect_index(_ptr(ib), ib.size, C.byref(nl), _ptr(lens), _ptr(degs), _ptr(widths), 64))
+    return [(int(lens[i]), int(degs[i]), int(widths[i])) for i in range(nl.value)]
+
+
+def decode_layer(index_bytes, layer):
+    """Host-only: the fixed-width u32 rows (padded with 0xFFFFFFFF) the loader stages in HBM for `layer`."""
+    shape = inspect_index(index_bytes)
+    n, _, w = shape[layer]
+    ib = np.frombuffer(index_bytes, dtype=np.uint8)
+    rows = np.empty((n, w), dtype=np.uint32)
+    _check(load_library().granne_b200_decode_layer(_ptr(ib), ib.size, layer, _ptr(rows), rows.size))
+    return rows
+
+
+def merge_topk_device(device, part_ids, part_dists, part_base, out_ids=None, out_dists=None, stream=None):
+    """granne_b200_merge_topk_device over CUDA torch tensors: part_ids int32 [P, nq, k] (u32 bits), part_dists
+    float32 [P, nq, k], part_base list of P global id offsets.  Returns (int64 [nq,k] global ids, float32 dists)."""
+    import torch
+
+    P, nq, k = part_ids.shape
+    if out_ids is None:
+        out_ids = torch.empty((nq, k), dtype=torch.int64, device=part_ids.device)
+        out_dists = torch.empty((nq, k), dtype=torch.float32, device=part_ids.device)
+    base = np.ascontiguousarray(part_base, dtype=np.uint64)
+    s = stream if stream is not None else torch.cuda.current_stream(part_ids.device).cuda_stream
+    _check(load_library().granne_b200_merge_topk_device(
+        device, C.c_void_p(part_ids.data_ptr()), C.c_void_p(part_dists.data_ptr()), _ptr(base), P, nq, k,
+        C.c_void_p(out_ids.data_ptr()), C.c_void_p(out_dists.data_ptr()), C.c_void_p(s)))
+    return out_ids, out_dists

@@ -1,0 +1,738 @@
+// granne_b200.cu — host side of the C ABI declared in include/granne_b200.h: loads granne's files, stages the layer
+// graph and the element vectors in HBM, and runs batched Granne::search on the device.
+//
+// Mirrors the reference's `Granne` (src/index/mod.rs:38-160) + `Index` trait (:54-104) for the three element kinds
+// (src/elements/angular.rs, angular_int.rs, embeddings/mod.rs).  There is no CPU search path in this library.
+#include "../../include/granne_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "formats.hpp"
+#include "search_kernels.cuh"
+
+namespace gb = granne_b200;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+
+#define GB_CUDA(expr)                                                                                   \
+    do {                                                                                                \
+        cudaError_t _e = (expr);                                                                        \
+        if (_e != cudaSuccess) {                                                                        \
+            return fail(GRANNE_B200_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));      \
+        }                                                                                               \
+    } while (0)
+
+// Per-call scratch: device copies of queries/results, status words, stream.  Pooled per handle so that several host
+// threads can search concurrently (the reference's `search` is `&self` and reentrant).
+struct Workspace {
+    cudaStream_t stream = nullptr;
+    void* d_queries = nullptr;
+    size_t queries_cap = 0;
+    uint32_t* d_ids = nullptr;
+    float* d_dists = nullptr;
+    uint32_t* d_counts = nullptr;
+    unsigned long long* d_stats = nullptr;
+    size_t out_cap_q = 0, out_cap_k = 0;
+    int* d_status = nullptr;  // nq ints
+    size_t status_cap = 0;
+    unsigned int* d_counters = nullptr;  // [0]=fast work counter, [1]=slow work counter
+    int* d_error = nullptr;              // [0]=sticky error bits of this call, [1]=overflow seen
+    void* h_pinned = nullptr;            // staging for host<->device copies
+    size_t pinned_cap = 0;
+    // slow path
+    unsigned long long* d_slow_list = nullptr;
+    uint32_t* d_slow_vis = nullptr;
+};
+
+}  // namespace
+
+struct granne_b200_index {
+    int device = 0;
+    int num_sms = 0;
+    size_t smem_optin = 0;
+    gb::DeviceIndex dev{};
+    std::vector<void*> allocations;
+    uint64_t device_bytes = 0;
+    uint64_t index_len = 0;  // Index::len
+    std::vector<uint32_t> layer_max_degree;
+    std::atomic<uint64_t> launches{0};
+    std::atomic<int> sticky_error{0};
+    std::mutex pool_mu;
+    std::vector<std::unique_ptr<Workspace>> pool;                     // host-pointer API: one per concurrent call
+    std::map<cudaStream_t, std::unique_ptr<Workspace>> stream_ws;     // device-pointer API: one per caller stream
+    // slow path sizing
+    uint32_t slow_ctas = 4;
+    uint32_t slow_list_cap = 32768;
+    uint32_t slow_vis_slots = 0;
+};
+
+namespace {
+
+using Handle = granne_b200_index;
+
+int check_device(int device, int* num_sms, size_t* smem_optin) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(GRANNE_B200_ERR_NO_DEVICE,
+                    std::string("no CUDA device available (granne_b200 has no CPU fallback): ") +
+                        (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    if (device < 0 || device >= count) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "device ordinal out of range");
+    cudaDeviceProp prop{};
+    GB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(GRANNE_B200_ERR_NO_DEVICE,
+                    std::string("device ") + prop.name + " is not sm_100 class; this library is built for sm_100a only");
+    *num_sms = prop.multiProcessorCount;
+    *smem_optin = prop.sharedMemPerBlockOptin;
+    return GRANNE_B200_OK;
+}
+
+template <class T>
+int dev_alloc(Handle* h, T** out, size_t count) {
+    void* p = nullptr;
+    const size_t bytes = std::max<size_t>(count * sizeof(T), 16);
+    GB_CUDA(cudaMalloc(&p, bytes));
+    h->allocations.push_back(p);
+    h->device_bytes += bytes;
+    *out = static_cast<T*>(p);
+    return GRANNE_B200_OK;
+}
+
+// Uploads `nrows` dense rows in slabs through a temporary device buffer and re-lays them out on the device.
+int stage_dense(Handle* h, const uint8_t* host_rows, uint64_t nrows, uint32_t dim, bool is_i8) {
+    gb::DeviceIndex& d = h->dev;
+    d.dim = dim;
+    d.full = dim / 32;
+    d.tail = dim % 32;
+    d.num_vectors = nrows;
+    if (is_i8) {
+        d.vec_group = 1;
+        d.row_stride = (dim + 15u) & ~15u;
+        int8_t* dst = nullptr;
+        int rc = dev_alloc(h, &dst, (size_t)nrows * d.row_stride);
+        if (rc) return rc;
+        d.vectors = dst;
+        const uint64_t slab = std::max<uint64_t>(1, (64ull << 20) / dim);
+        int8_t* tmp = nullptr;
+        GB_CUDA(cudaMalloc(&tmp, (size_t)std::min(slab, std::max<uint64_t>(nrows, 1)) * dim));
+        for (uint64_t r0 = 0; r0 < nrows; r0 += slab) {
+            const uint64_t nr = std::min(slab, nrows - r0);
+            GB_CUDA(cudaMemcpy(tmp, host_rows + r0 * dim, (size_t)nr * dim, cudaMemcpyHostToDevice));
+            gb::pad_rows_i8_kernel<<<h->num_sms * 8, 256>>>(tmp, dst + r0 * d.row_stride, nr, dim, d.row_stride);
+            h->launches++;
+            GB_CUDA(cudaGetLastError());
+        }
+        GB_CUDA(cudaDeviceSynchronize());
+        GB_CUDA(cudaFree(tmp));
+    } else {
+        const uint32_t full = d.full;
+        const bool templated = (full <= 4 || full == 6 || full == 8) && h->dev.kind == gb::kAngularF32;
+        d.vec_group = !templated || full == 0 ? 1 : (full % 4 == 0 ? 4 : (full % 2 == 0 ? 2 : 1));
+        d.row_stride = (dim + 3u) & ~3u;
+        float* dst = nullptr;
+        int rc = dev_alloc(h, &dst, (size_t)nrows * d.row_stride);
+        if (rc) return rc;
+        d.vectors = dst;
+        const uint64_t slab = std::max<uint64_t>(1, (64ull << 20) / (dim * 4ull));
+        float* tmp = nullptr;
+        GB_CUDA(cudaMalloc(&tmp, (size_t)std::min(slab, std::max<uint64_t>(nrows, 1)) * dim * 4));
+        const float* src = reinterpret_cast<const float*>(host_rows);
+        for (uint64_t r0 = 0; r0 < nrows; r0 += slab) {
+            const uint64_t nr = std::min(slab, nrows - r0);
+            GB_CUDA(cudaMemcpy(tmp, src + r0 * dim, (size_t)nr * dim * 4, cudaMemcpyHostToDevice));
+            gb::permute_rows_f32_kernel<<<h->num_sms * 8, 256>>>(tmp, dst + r0 * d.row_stride, nr, dim, full,
+                                                                 d.vec_group, d.row_stride);
+            h->launches++;
+            GB_CUDA(cudaGetLastError());
+        }
+        GB_CUDA(cudaDeviceSynchronize());
+        GB_CUDA(cudaFree(tmp));
+    }
+    return GRANNE_B200_OK;
+}
+
+int open_impl(const uint8_t* index_bytes, size_t index_len, int kind, const uint8_t* el, size_t el_len,
+              const uint8_t* emb, size_t emb_len, int device, Handle** out) {
+    if (!out) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "out handle pointer is null");
+    *out = nullptr;
+    if (!index_bytes || !el) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "index/elements buffer is null");
+    if (kind != GRANNE_B200_ANGULAR && kind != GRANNE_B200_ANGULAR_INT && kind != GRANNE_B200_EMBEDDINGS)
+        return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "Invalid element type");
+    if (kind == GRANNE_B200_EMBEDDINGS && !emb)
+        return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "embeddings buffer required for this element type");
+
+    std::unique_ptr<Handle> h(new Handle());
+    int rc = check_device(device, &h->num_sms, &h->smem_optin);
+    if (rc) return rc;
+    h->device = device;
+    GB_CUDA(cudaSetDevice(device));
+
+    std::string err;
+    gb::HostGraph graph;
+    if (!gb::parse_index(index_bytes, index_len, &graph, &err)) return fail(GRANNE_B200_ERR_FORMAT, err);
+    if (graph.layers.size() > (size_t)gb::kMaxLayers) return fail(GRANNE_B200_ERR_FORMAT, "too many layers");
+
+    gb::DeviceIndex& d = h->dev;
+    d.kind = kind;
+    if (kind == GRANNE_B200_EMBEDDINGS) {
+        gb::DenseView ev;
+        if (!gb::parse_dense(emb, emb_len, 4, &ev, &err)) return fail(GRANNE_B200_ERR_FORMAT, "embeddings: " + err);
+        gb::SumElements se;
+        if (!gb::parse_sum_elements(el, el_len, &se, &err)) return fail(GRANNE_B200_ERR_FORMAT, err);
+        for (uint32_t t : se.terms)
+            if (t >= ev.num) return fail(GRANNE_B200_ERR_FORMAT, "element refers to a missing embedding id");
+        if (ev.dim > 4096) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "embeddings wider than 4096 are unsupported");
+        rc = stage_dense(h.get(), ev.data, ev.num, (uint32_t)ev.dim, false);
+        if (rc) return rc;
+        d.num_elements = se.offsets.size() - 1;
+        unsigned long long* doff = nullptr;
+        uint32_t* dterms = nullptr;
+        if ((rc = dev_alloc(h.get(), &doff, se.offsets.size()))) return rc;
+        if ((rc = dev_alloc(h.get(), &dterms, se.terms.size()))) return rc;
+        GB_CUDA(cudaMemcpy(doff, se.offsets.data(), se.offsets.size() * 8, cudaMemcpyHostToDevice));
+        if (!se.terms.empty())
+            GB_CUDA(cudaMemcpy(dterms, se.terms.data(), se.terms.size() * 4, cudaMemcpyHostToDevice));
+        d.sum_offsets = doff;
+        d.sum_terms = dterms;
+    } else {
+        gb::DenseView dv;
+        const bool i8 = kind == GRANNE_B200_ANGULAR_INT;
+        if (!gb::parse_dense(el, el_len, i8 ? 1 : 4, &dv, &err)) return fail(GRANNE_B200_ERR_FORMAT, err);
+        if (dv.dim > 16384) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "vectors wider than 16384 are unsupported");
+        rc = stage_dense(h.get(), dv.data, dv.num, (uint32_t)dv.dim, i8);
+        if (rc) return rc;
+        d.num_elements = dv.num;
+    }
+
+    d.num_layers = (int)graph.layers.size();
+    for (int l = 0; l < d.num_layers; ++l) {
+        const gb::HostLayer& L = graph.layers[l];
+        if (L.num_nodes > d.num_elements)
+            return fail(GRANNE_B200_ERR_FORMAT, "index refers to more elements than the container holds");
+        uint32_t* rows = nullptr;
+        if ((rc = dev_alloc(h.get(), &rows, L.rows.size()))) return rc;
+        if (!L.rows.empty()) GB_CUDA(cudaMemcpy(rows, L.rows.data(), L.rows.size() * 4, cudaMemcpyHostToDevice));
+        d.layer_rows[l] = rows;
+        d.layer_width[l] = L.width;
+        d.layer_len[l] = L.num_nodes;
+        h->layer_max_degree.push_back(L.max_degree);
+    }
+    h->index_len = d.num_layers ? graph.layers.back().num_nodes : 0;
+    // slow-path visited table: large enough for every node of the bottom layer (capped)
+    const uint64_t want = h->index_len + h->index_len / 7 + 1024;
+    h->slow_vis_slots = (uint32_t)std::min<uint64_t>(want, 16ull << 20);
+    *out = h.release();
+    return GRANNE_B200_OK;
+}
+
+int read_file(const char* path, std::vector<uint8_t>* out) {
+    if (!path) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "path is null");
+    std::ifstream f(path, std::ios::binary | std::ios::ate);
+    if (!f) return fail(GRANNE_B200_ERR_IO, std::string("Could not open ") + path);
+    const std::streamsize n = f.tellg();
+    f.seekg(0);
+    out->resize((size_t)n);
+    if (n > 0 && !f.read(reinterpret_cast<char*>(out->data()), n))
+        return fail(GRANNE_B200_ERR_IO, std::string("Could not read ") + path);
+    return GRANNE_B200_OK;
+}
+
+// ---- launch configuration -----------------------------------------------------------------------------------------
+struct LaunchPlan {
+    uint32_t list_cap, vis_slots, vis_upper;
+    size_t smem;
+};
+
+LaunchPlan make_plan(const Handle* h, uint32_t max_search) {
+    const gb::DeviceIndex& d = h->dev;
+    LaunchPlan p;
+    p.list_cap = std::max<uint32_t>(32, (max_search + 16 + 31) & ~31u);
+    const uint32_t deg = h->layer_max_degree.empty() ? 1 : std::max<uint32_t>(8, h->layer_max_degree.back());
+    uint64_t want = std::max<uint64_t>(1024, (uint64_t)max_search * std::min<uint32_t>(deg, 64));
+    want = (want + 31) & ~31ull;
+    const uint32_t qbytes = (d.kind == gb::kAngularI8) ? d.row_stride : ((d.dim + 3u) & ~3u) * 4u;
+    const size_t fixed = 32 * 33 * 4 + ((qbytes + 15u) & ~15u) * (d.kind == gb::kSumEmbeddings ? 2 : 1) +
+                         (size_t)p.list_cap * 8;
+    const size_t budget = h->smem_optin;
+    if (fixed + 4096 > budget) {  // caller rejects: the candidate list alone does not fit
+        p.vis_slots = p.vis_upper = 0;
+        p.smem = 0;
+        return p;
+    }
+    if (fixed + want * 4 > budget) want = (budget - fixed) / 4 / 32 * 32;  // huge max_search: overflow -> slow path
+    p.vis_slots = (uint32_t)want;
+    p.vis_upper = std::min<uint32_t>(1024, p.vis_slots);
+    p.smem = fixed + (size_t)p.vis_slots * 4;
+    return p;
+}
+
+template <class Dist>
+int launch_search(Handle* h, const gb::SearchArgs& a, const LaunchPlan& plan, cudaStream_t stream) {
+    auto kern = gb::search_kernel<Dist>;
+    static std::atomic<bool> attr_set{false};
+    if (!attr_set.load()) {
+        GB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
+        attr_set.store(true);
+    }
+    // fast pass
+    static std::mutex occ_mu;
+    static std::map<size_t, int> occ_cache;
+    int occ = 0;
+    {
+        std::lock_guard<std::mutex> g(occ_mu);
+        auto it = occ_cache.find(plan.smem);
+        if (it == occ_cache.end()) {
+            GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32, plan.smem));
+            occ_cache[plan.smem] = occ;
+        } else {
+            occ = it->second;
+        }
+    }
+    if (occ < 1) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "max_search too large for the shared-memory workspace");
+    const unsigned long long slots = (unsigned long long)occ * h->num_sms;
+    const unsigned grid = (unsigned)std::min<unsigned long long>(a.nq, slots);
+    kern<<<grid, 32, plan.smem, stream>>>(h->dev, a);
+    h->launches++;
+    GB_CUDA(cudaGetLastError());
+    // slow pass: re-runs only the queries the fast pass flagged (exits immediately if none)
+    gb::SearchArgs s = a;
+    s.slow_pass = 1;
+    s.work_counter = a.work_counter + 1;
+    const size_t slow_smem = plan.smem - (size_t)plan.vis_slots * 4 - (size_t)plan.list_cap * 8;
+    kern<<<h->slow_ctas, 32, slow_smem, stream>>>(h->dev, s);
+    h->launches++;
+    GB_CUDA(cudaGetLastError());
+    return GRANNE_B200_OK;
+}
+
+int dispatch_search(Handle* h, const gb::SearchArgs& a, const LaunchPlan& plan, cudaStream_t stream) {
+    const gb::DeviceIndex& d = h->dev;
+    switch (d.kind) {
+        case gb::kAngularI8:
+            return launch_search<gb::DistI8>(h, a, plan, stream);
+        case gb::kSumEmbeddings:
+            return launch_search<gb::DistSum>(h, a, plan, stream);
+        default:
+            break;
+    }
+    if (d.vec_group == 1 && d.full > 4) return launch_search<gb::DistF32Generic>(h, a, plan, stream);
+    switch (d.full) {
+        case 0: return launch_search<gb::DistF32<0>>(h, a, plan, stream);
+        case 1: return launch_search<gb::DistF32<1>>(h, a, plan, stream);
+        case 2: return launch_search<gb::DistF32<2>>(h, a, plan, stream);
+        case 3: return launch_search<gb::DistF32<3>>(h, a, plan, stream);
+        case 4: return launch_search<gb::DistF32<4>>(h, a, plan, stream);
+        case 6: return launch_search<gb::DistF32<6>>(h, a, plan, stream);
+        case 8: return launch_search<gb::DistF32<8>>(h, a, plan, stream);
+        default: return launch_search<gb::DistF32Generic>(h, a, plan, stream);
+    }
+}
+
+// ---- workspace pool -----------------------------------------------------------------------------------------------
+int ws_acquire(Handle* h, Workspace** out) {
+    {
+        std::lock_guard<std::mutex> g(h->pool_mu);
+        if (!h->pool.empty()) {
+            *out = h->pool.back().release();
+            h->pool.pop_back();
+            return GRANNE_B200_OK;
+        }
+    }
+    std::unique_ptr<Workspace> w(new Workspace());
+    GB_CUDA(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
+    GB_CUDA(cudaMalloc(&w->d_counters, 4 * sizeof(unsigned int)));
+    GB_CUDA(cudaMalloc(&w->d_error, 4 * sizeof(int)));
+    GB_CUDA(cudaMalloc(&w->d_slow_list, (size_t)h->slow_ctas * h->slow_list_cap * 8));
+    GB_CUDA(cudaMalloc(&w->d_slow_vis, (size_t)h->slow_ctas * h->slow_vis_slots * 4));
+    *out = w.release();
+    return GRANNE_B200_OK;
+}
+void ws_release(Handle* h, Workspace* w) {
+    std::lock_guard<std::mutex> g(h->pool_mu);
+    h->pool.emplace_back(w);
+}
+void ws_destroy(Workspace* w) {
+    if (!w) return;
+    cudaFree(w->d_queries);
+    cudaFree(w->d_ids);
+    cudaFree(w->d_dists);
+    cudaFree(w->d_counts);
+    cudaFree(w->d_stats);
+    cudaFree(w->d_status);
+    cudaFree(w->d_counters);
+    cudaFree(w->d_error);
+    cudaFree(w->d_slow_list);
+    cudaFree(w->d_slow_vis);
+    if (w->h_pinned) cudaFreeHost(w->h_pinned);
+    if (w->stream) cudaStreamDestroy(w->stream);
+}
+
+int ws_reserve(Workspace* w, size_t query_bytes, size_t nq, size_t k) {
+    if (query_bytes > w->queries_cap) {
+        cudaFree(w->d_queries);
+        w->d_queries = nullptr;
+        w->queries_cap = 0;
+        GB_CUDA(cudaMalloc(&w->d_queries, query_bytes));
+        w->queries_cap = query_bytes;
+    }
+    if (nq * k > w->out_cap_q * w->out_cap_k || nq > w->out_cap_q) {
+        cudaFree(w->d_ids);
+        cudaFree(w->d_dists);
+        cudaFree(w->d_counts);
+        cudaFree(w->d_stats);
+        w->d_ids = nullptr, w->d_dists = nullptr, w->d_counts = nullptr, w->d_stats = nullptr;
+        w->out_cap_q = w->out_cap_k = 0;
+        GB_CUDA(cudaMalloc(&w->d_ids, std::max<size_t>(nq * k, 1) * 4));
+        GB_CUDA(cudaMalloc(&w->d_dists, std::max<size_t>(nq * k, 1) * 4));
+        GB_CUDA(cudaMalloc(&w->d_counts, std::max<size_t>(nq, 1) * 4));
+        GB_CUDA(cudaMalloc(&w->d_stats, std::max<size_t>(nq, 1) * 4 * 8));
+        w->out_cap_q = nq;
+        w->out_cap_k = k;
+    }
+    const size_t pinned = query_bytes + nq * k * 8 + nq * 4 + nq * 32 + 128;
+    if (pinned > w->pinned_cap) {
+        if (w->h_pinned) cudaFreeHost(w->h_pinned);
+        w->h_pinned = nullptr;
+        w->pinned_cap = 0;
+        GB_CUDA(cudaMallocHost(&w->h_pinned, pinned));
+        w->pinned_cap = pinned;
+    }
+    return GRANNE_B200_OK;
+}
+
+int ws_reserve_status(Workspace* w, size_t nq) {
+    if (nq > w->status_cap) {
+        cudaFree(w->d_status);
+        w->d_status = nullptr;
+        w->status_cap = 0;
+        GB_CUDA(cudaMalloc(&w->d_status, std::max<size_t>(nq, 1) * sizeof(int)));
+        w->status_cap = nq;
+    }
+    return GRANNE_B200_OK;
+}
+
+int validate_search(const Handle* h, const void* q, size_t nq, int fmt, uint32_t max_search, uint32_t k,
+                    const void* ids, const void* dists) {
+    if (!h) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "index handle is null");
+    if (fmt != GRANNE_B200_QUERY_RAW_F32 && fmt != GRANNE_B200_QUERY_ELEMENT)
+        return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "unknown query format");
+    if (max_search == 0)
+        return fail(GRANNE_B200_ERR_INVALID_ARGUMENT,
+                    "max_search must be >= 1 (the reference panics on 0, src/index/mod.rs:1019)");
+    if (nq > 0xFFFFFFF0ull) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "too many queries in one batch");
+    if (nq && (!q || (k && (!ids || !dists)))) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "null buffer");
+    return GRANNE_B200_OK;
+}
+
+// Enqueues one batch on `stream` with device pointers.  Needs a workspace for status words / slow path.
+int enqueue_search(Handle* h, Workspace* w, const void* d_queries, size_t nq, int fmt, uint32_t max_search,
+                   uint32_t k, uint32_t* d_ids, float* d_dists, uint32_t* d_counts, unsigned long long* d_stats,
+                   cudaStream_t stream, bool reset_error) {
+    const LaunchPlan plan = make_plan(h, max_search);
+    if (plan.smem == 0 || max_search + 64 > h->slow_list_cap)
+        return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "max_search exceeds the supported maximum (about 27000)");
+    int rc = ws_reserve_status(w, nq);
+    if (rc) return rc;
+    GB_CUDA(cudaMemsetAsync(w->d_counters, 0, 4 * sizeof(unsigned int), stream));
+    if (reset_error) GB_CUDA(cudaMemsetAsync(w->d_error, 0, 4 * sizeof(int), stream));
+    GB_CUDA(cudaMemsetAsync(w->d_status, 0xFF, nq * sizeof(int), stream));
+    gb::SearchArgs a{};
+    a.queries = d_queries;
+    a.query_format = fmt;
+    a.nq = nq;
+    a.max_search = max_search;
+    a.num_neighbors = k;
+    a.list_cap = plan.list_cap;
+    a.vis_slots = plan.vis_slots;
+    a.vis_slots_upper = plan.vis_upper;
+    a.out_ids = d_ids;
+    a.out_dists = d_dists;
+    a.out_counts = d_counts;
+    a.out_stats = d_stats;
+    a.query_status = w->d_status;
+    a.work_counter = w->d_counters;
+    a.error_flag = w->d_error;
+    a.slow_list = w->d_slow_list;
+    a.slow_visited = w->d_slow_vis;
+    a.slow_list_cap = h->slow_list_cap;
+    a.slow_vis_slots = h->slow_vis_slots;
+    a.slow_pass = 0;
+    return dispatch_search(h, a, plan, stream);
+}
+
+int error_from_bits(int bits) {
+    if (bits & gb::kStatusNotFinite)
+        return fail(GRANNE_B200_ERR_NOT_FINITE, "a NaN distance occurred (non-finite query or element)");
+    if (bits & gb::kStatusOverflow)
+        return fail(GRANNE_B200_ERR_CAPACITY, "exact search workspace exhausted even on the slow path");
+    return GRANNE_B200_OK;
+}
+
+}  // namespace
+
+// =================================================================================================================
+// C ABI
+// =================================================================================================================
+extern "C" {
+
+int granne_b200_abi_version(void) { return GRANNE_B200_ABI_VERSION; }
+
+const char* granne_b200_last_error(void) { return g_last_error.c_str(); }
+
+int granne_b200_open(const void* index_bytes, size_t index_len, int element_kind, const void* elements_bytes,
+                     size_t elements_len, const void* embeddings_bytes, size_t embeddings_len, int device,
+                     granne_b200_index** out) {
+    try {
+        return open_impl(static_cast<const uint8_t*>(index_bytes), index_len, element_kind,
+                         static_cast<const uint8_t*>(elements_bytes), elements_len,
+                         static_cast<const uint8_t*>(embeddings_bytes), embeddings_len, device, out);
+    } catch (const std::exception& e) {
+        return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, std::string("exception: ") + e.what());
+    }
+}
+
+int granne_b200_open_files(const char* index_path, int element_kind, const char* elements_path,
+                           const char* embeddings_path, int device, granne_b200_index** out) {
+    try {
+        std::vector<uint8_t> ib, eb, mb;
+        int rc;
+        if ((rc = read_file(index_path, &ib))) return rc;
+        if ((rc = read_file(elements_path, &eb))) return rc;
+        if (element_kind == GRANNE_B200_EMBEDDINGS) {
+            if (!embeddings_path)
+                return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "embeddings_path required for this element type!");
+            if ((rc = read_file(embeddings_path, &mb))) return rc;
+        }
+        return open_impl(ib.data(), ib.size(), element_kind, eb.data(), eb.size(), mb.empty() ? nullptr : mb.data(),
+                         mb.size(), device, out);
+    } catch (const std::exception& e) {
+        return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, std::string("exception: ") + e.what());
+    }
+}
+
+void granne_b200_close(granne_b200_index* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (auto& w : h->pool) ws_destroy(w.get());
+    h->pool.clear();
+    for (auto& kv : h->stream_ws) ws_destroy(kv.second.get());
+    h->stream_ws.clear();
+    for (void* p : h->allocations) cudaFree(p);
+    delete h;
+}
+
+uint64_t granne_b200_len(const granne_b200_index* h) { return h ? h->index_len : 0; }
+uint64_t granne_b200_num_layers(const granne_b200_index* h) { return h ? (uint64_t)h->dev.num_layers : 0; }
+uint64_t granne_b200_layer_len(const granne_b200_index* h, uint64_t layer) {
+    if (!h || layer >= (uint64_t)h->dev.num_layers) return 0;
+    return h->dev.layer_len[layer];
+}
+uint64_t granne_b200_num_elements(const granne_b200_index* h) { return h ? h->dev.num_elements : 0; }
+uint64_t granne_b200_dim(const granne_b200_index* h) { return h ? h->dev.dim : 0; }
+int granne_b200_element_kind(const granne_b200_index* h) { return h ? h->dev.kind : -1; }
+uint64_t granne_b200_launch_count(const granne_b200_index* h) { return h ? h->launches.load() : 0; }
+uint64_t granne_b200_device_bytes(const granne_b200_index* h) { return h ? h->device_bytes : 0; }
+
+int granne_b200_get_neighbors(const granne_b200_index* h, uint64_t idx, uint64_t layer, uint32_t* out, size_t cap,
+                              size_t* out_n) {
+    if (!h || !out_n) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "null argument");
+    if (layer >= (uint64_t)h->dev.num_layers || idx >= h->dev.layer_len[layer])
+        return fail(GRANNE_B200_ERR_OUT_OF_RANGE, "node or layer out of range");
+    GB_CUDA(cudaSetDevice(h->device));
+    const uint32_t w = h->dev.layer_width[layer];
+    std::vector<uint32_t> row(w);
+    GB_CUDA(cudaMemcpy(row.data(), h->dev.layer_rows[layer] + idx * w, w * 4, cudaMemcpyDeviceToHost));
+    size_t n = 0;
+    while (n < w && row[n] != gb::kUnusedId) ++n;
+    *out_n = n;
+    for (size_t i = 0; i < n && i < cap && out; ++i) out[i] = row[i];
+    return GRANNE_B200_OK;
+}
+
+int granne_b200_get_element(const granne_b200_index* hc, uint64_t idx, void* out) {
+    granne_b200_index* h = const_cast<granne_b200_index*>(hc);
+    if (!h || !out) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "null argument");
+    if (idx >= h->dev.num_elements) return fail(GRANNE_B200_ERR_OUT_OF_RANGE, "element index out of range");
+    GB_CUDA(cudaSetDevice(h->device));
+    const size_t bytes = h->dev.kind == gb::kAngularI8 ? h->dev.dim : (size_t)h->dev.dim * 4;
+    void* d = nullptr;
+    GB_CUDA(cudaMalloc(&d, bytes));
+    gb::get_element_kernel<<<1, 32>>>(h->dev, idx, d);
+    h->launches++;
+    cudaError_t e = cudaMemcpy(out, d, bytes, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    GB_CUDA(e);
+    return GRANNE_B200_OK;
+}
+
+int granne_b200_search_batch_device(granne_b200_index* h, const void* d_queries, size_t nq, int query_format,
+                                    uint32_t max_search, uint32_t num_neighbors, uint32_t* d_out_ids,
+                                    float* d_out_dists, uint32_t* d_out_counts, uint64_t* d_out_stats,
+                                    void* cuda_stream) {
+    int rc = validate_search(h, d_queries, nq, query_format, max_search, num_neighbors, d_out_ids, d_out_dists);
+    if (rc) return rc;
+    if (nq == 0) return GRANNE_B200_OK;
+    GB_CUDA(cudaSetDevice(h->device));
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    // One workspace per caller stream: calls on the same stream are serialised by the stream itself, so the status
+    // words / slow-path buffers can be reused; the error word stays sticky until granne_b200_stream_status().
+    Workspace* w = nullptr;
+    {
+        std::lock_guard<std::mutex> g(h->pool_mu);
+        auto it = h->stream_ws.find(stream);
+        if (it != h->stream_ws.end()) w = it->second.get();
+    }
+    if (!w) {
+        if ((rc = ws_acquire(h, &w))) return rc;
+        GB_CUDA(cudaMemset(w->d_error, 0, 4 * sizeof(int)));
+        std::lock_guard<std::mutex> g(h->pool_mu);
+        h->stream_ws[stream] = std::unique_ptr<Workspace>(w);
+    }
+    return enqueue_search(h, w, d_queries, nq, query_format, max_search, num_neighbors, d_out_ids, d_out_dists,
+                          d_out_counts, reinterpret_cast<unsigned long long*>(d_out_stats), stream, false);
+}
+
+int granne_b200_stream_status(granne_b200_index* h) {
+    if (!h) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "index handle is null");
+    GB_CUDA(cudaSetDevice(h->device));
+    GB_CUDA(cudaDeviceSynchronize());
+    int bits = h->sticky_error.exchange(0);
+    std::lock_guard<std::mutex> g(h->pool_mu);
+    for (auto& kv : h->stream_ws) {
+        int e[4] = {0, 0, 0, 0};
+        GB_CUDA(cudaMemcpy(e, kv.second->d_error, sizeof(e), cudaMemcpyDeviceToHost));
+        bits |= e[0];
+        GB_CUDA(cudaMemset(kv.second->d_error, 0, sizeof(e)));
+    }
+    return error_from_bits(bits);
+}
+
+int granne_b200_search_batch(granne_b200_index* h, const void* queries, size_t nq, int query_format,
+                             uint32_t max_search, uint32_t num_neighbors, uint32_t* out_ids, float* out_dists,
+                             uint32_t* out_counts, uint64_t* out_stats) {
+    int rc = validate_search(h, queries, nq, query_format, max_search, num_neighbors, out_ids, out_dists);
+    if (rc) return rc;
+    if (nq == 0) return GRANNE_B200_OK;
+    GB_CUDA(cudaSetDevice(h->device));
+    const size_t k = num_neighbors;
+    const bool i8q = h->dev.kind == gb::kAngularI8 && query_format == GRANNE_B200_QUERY_ELEMENT;
+    const size_t qbytes = nq * h->dev.dim * (i8q ? 1 : 4);
+    Workspace* w = nullptr;
+    if ((rc = ws_acquire(h, &w))) return rc;
+    struct Releaser {
+        Handle* h;
+        Workspace* w;
+        ~Releaser() { ws_release(h, w); }
+    } rel{h, w};
+    if ((rc = ws_reserve(w, qbytes, nq, k))) return rc;
+    // pinned staging layout: queries | ids | dists | counts | stats | error
+    uint8_t* hp = static_cast<uint8_t*>(w->h_pinned);
+    uint8_t* hq = hp;
+    uint32_t* hids = reinterpret_cast<uint32_t*>(hp + ((qbytes + 15) & ~size_t(15)));
+    float* hd = reinterpret_cast<float*>(hids + nq * k);
+    uint32_t* hc = reinterpret_cast<uint32_t*>(hd + nq * k);
+    int* herr = reinterpret_cast<int*>(hc + nq);
+    unsigned long long* hstats = reinterpret_cast<unsigned long long*>(
+        reinterpret_cast<uint8_t*>(hp) + ((reinterpret_cast<uint8_t*>(herr + 4) - hp + 15) & ~size_t(15)));
+    // (pinned_cap was sized with slack for the alignment above)
+    std::memcpy(hq, queries, qbytes);
+    GB_CUDA(cudaMemcpyAsync(w->d_queries, hq, qbytes, cudaMemcpyHostToDevice, w->stream));
+    rc = enqueue_search(h, w, w->d_queries, nq, query_format, max_search, num_neighbors, w->d_ids, w->d_dists,
+                        w->d_counts, out_stats ? w->d_stats : nullptr, w->stream, true);
+    if (rc) return rc;
+    if (k) {
+        GB_CUDA(cudaMemcpyAsync(hids, w->d_ids, nq * k * 4, cudaMemcpyDeviceToHost, w->stream));
+        GB_CUDA(cudaMemcpyAsync(hd, w->d_dists, nq * k * 4, cudaMemcpyDeviceToHost, w->stream));
+    }
+    GB_CUDA(cudaMemcpyAsync(hc, w->d_counts, nq * 4, cudaMemcpyDeviceToHost, w->stream));
+    GB_CUDA(cudaMemcpyAsync(herr, w->d_error, 4 * sizeof(int), cudaMemcpyDeviceToHost, w->stream));
+    if (out_stats) GB_CUDA(cudaMemcpyAsync(hstats, w->d_stats, nq * 32, cudaMemcpyDeviceToHost, w->stream));
+    GB_CUDA(cudaStreamSynchronize(w->stream));
+    if (out_stats) std::memcpy(out_stats, hstats, nq * 32);
+    if (k) {
+        std::memcpy(out_ids, hids, nq * k * 4);
+        std::memcpy(out_dists, hd, nq * k * 4);
+    }
+    if (out_counts) std::memcpy(out_counts, hc, nq * 4);
+    return error_from_bits(herr[0]);
+}
+
+int granne_b200_inspect_index(const void* index_bytes, size_t index_len, uint64_t* out_num_layers,
+                              uint64_t* out_layer_len, uint32_t* out_max_degree, uint32_t* out_row_width, size_t cap) {
+    if (!index_bytes || !out_num_layers) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "null argument");
+    try {
+        gb::HostGraph graph;
+        std::string err;
+        if (!gb::parse_index(static_cast<const uint8_t*>(index_bytes), index_len, &graph, &err))
+            return fail(GRANNE_B200_ERR_FORMAT, err);
+        *out_num_layers = graph.layers.size();
+        for (size_t l = 0; l < graph.layers.size() && l < cap; ++l) {
+            if (out_layer_len) out_layer_len[l] = graph.layers[l].num_nodes;
+            if (out_max_degree) out_max_degree[l] = graph.layers[l].max_degree;
+            if (out_row_width) out_row_width[l] = graph.layers[l].width;
+        }
+        return GRANNE_B200_OK;
+    } catch (const std::exception& e) {
+        return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, std::string("exception: ") + e.what());
+    }
+}
+
+int granne_b200_decode_layer(const void* index_bytes, size_t index_len, uint64_t layer, uint32_t* rows,
+                             size_t rows_cap_u32) {
+    if (!index_bytes || !rows) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "null argument");
+    try {
+        gb::HostGraph graph;
+        std::string err;
+        if (!gb::parse_index(static_cast<const uint8_t*>(index_bytes), index_len, &graph, &err))
+            return fail(GRANNE_B200_ERR_FORMAT, err);
+        if (layer >= graph.layers.size()) return fail(GRANNE_B200_ERR_OUT_OF_RANGE, "layer out of range");
+        const gb::HostLayer& L = graph.layers[layer];
+        if (L.rows.size() > rows_cap_u32) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "rows buffer too small");
+        std::memcpy(rows, L.rows.data(), L.rows.size() * 4);
+        return GRANNE_B200_OK;
+    } catch (const std::exception& e) {
+        return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, std::string("exception: ") + e.what());
+    }
+}
+
+int granne_b200_merge_topk_device(int device, const uint32_t* d_part_ids, const float* d_part_dists,
+                                  const uint64_t* part_base, size_t num_parts, size_t nq, uint32_t k,
+                                  uint64_t* d_out_ids, float* d_out_dists, void* cuda_stream) {
+    if (!d_part_ids || !d_part_dists || !part_base || !d_out_ids || !d_out_dists)
+        return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "null argument");
+    if (num_parts == 0 || num_parts > 64) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "num_parts must be 1..64");
+    if (nq == 0 || k == 0) return GRANNE_B200_OK;
+    GB_CUDA(cudaSetDevice(device));
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    unsigned long long* d_base = nullptr;
+    GB_CUDA(cudaMallocAsync(&d_base, num_parts * 8, stream));
+    GB_CUDA(cudaMemcpyAsync(d_base, part_base, num_parts * 8, cudaMemcpyHostToDevice, stream));
+    const unsigned block = 128, grid = (unsigned)((nq + block - 1) / block);
+    gb::merge_topk_kernel<<<grid, block, 0, stream>>>(d_part_ids, d_part_dists, d_base, (uint32_t)num_parts, nq, k,
+                                                      reinterpret_cast<unsigned long long*>(d_out_ids), d_out_dists);
+    GB_CUDA(cudaGetLastError());
+    GB_CUDA(cudaFreeAsync(d_base, stream));
+    return GRANNE_B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,848 @@
+// search_kernels.cuh — sm_100a kernels for granne's search path:
+//   Granne::search -> find_entrypoint -> search_for_neighbors -> ElementContainer::dist_to_element
+//   (reference: src/index/mod.rs:140-150, 962-1037; src/max_size_heap.rs; src/elements/*; src/math.rs)
+//
+// Execution model: one warp per query (one 32-thread CTA, several CTAs per SM, persistent over a work counter).
+// Per query the warp owns, in shared memory,
+//   * a sorted candidate list L (capacity C = max_search + slack) that merges the reference's two heaps:
+//     `res` (bounded max-heap of expanded nodes) and `pq` (unbounded min-heap frontier) — see "Exactness" below,
+//   * an exact visited set (open-addressing hash of u32 ids; the reference's FxHashSet),
+//   * a 32x33 f32 tile used to reproduce the reference's strictly ordered 32-lane partial-sum reduction.
+// Candidate vectors are gathered straight from HBM with fully coalesced 128-bit loads (the row layout in HBM is
+// lane-permuted so that one LDG.128 per lane fetches a whole 512-byte row), all rows of one expansion in flight at once.
+//
+// Exactness (bit-identical ids AND f32 distances, identical n_dist / n_expand counters):
+//   * dot_product_f32 (src/math.rs:16-42): lane i owns accumulator chunk[i]; FMA over chunks in order; the 32
+//     partials are then added in lane order by ONE lane per candidate (via the smem tile), then the FMA tail.
+//   * L keeps entries sorted by (distance bits, id) — the tuple order of (NotNan<f32>, usize).  Bit 63 of a key marks
+//     "expanded" (popped from pq and pushed to res); distances are >= +0 so the sign bit is free.
+//     Let E = expanded entries of L in order.  res == first max_search entries of E whenever |E| >= max_search;
+//     otherwise res is not full or still holds entries that were evicted from L, which are >= every entry of L, and in
+//     both cases the reference neither breaks nor filters anything that could later be expanded.
+//     An entry may be dropped from L only if at least max_search entries with STRICTLY smaller distance remain
+//     (such an entry can never be expanded nor reported).  If a drop is needed and that does not hold (a plateau of
+//     equal distances wider than the slack) the query is flagged and re-run on the slow path with a global-memory
+//     workspace (same code, larger capacities).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace granne_b200 {
+
+constexpr int kMaxLayers = 24;
+constexpr uint32_t kUnusedId = 0xFFFFFFFFu;
+constexpr unsigned long long kFlagExpanded = 1ull << 63;
+constexpr unsigned long long kKeyMask = ~kFlagExpanded;
+constexpr unsigned kFullMask = 0xFFFFFFFFu;
+
+enum ElementKind : int { kAngularF32 = 0, kAngularI8 = 1, kSumEmbeddings = 2 };
+enum QueryFormat : int { kQueryRawF32 = 0, kQueryElement = 1 };
+
+// per-query status bits (device side)
+constexpr int kStatusOverflow = 1;   // workspace too small for an exact answer -> slow path
+constexpr int kStatusNotFinite = 2;  // NaN distance (reference panics)
+
+// The staged index in HBM.
+struct DeviceIndex {
+    int kind;
+    uint32_t dim;
+    uint32_t full;        // dim / 32   (number of complete 32-wide chunks, src/math.rs:21)
+    uint32_t tail;        // dim % 32
+    uint32_t vec_group;   // V: chunks interleaved per lane in the permuted f32 row layout (4, 2 or 1)
+    uint32_t row_stride;  // f32: floats per row (multiple of 4); i8: bytes per row (multiple of 16)
+    const void* vectors;  // f32 rows (ANGULAR: elements; EMBEDDINGS: embedding table) or i8 rows
+    uint64_t num_vectors;
+    const unsigned long long* sum_offsets;  // EMBEDDINGS: num_elements + 1
+    const uint32_t* sum_terms;
+    uint64_t num_elements;
+    int num_layers;
+    const uint32_t* layer_rows[kMaxLayers];
+    uint32_t layer_width[kMaxLayers];
+    unsigned long long layer_len[kMaxLayers];
+};
+
+struct SearchArgs {
+    const void* queries;  // nq x dim (f32 or i8)
+    int query_format;
+    unsigned long long nq;
+    uint32_t max_search;
+    uint32_t num_neighbors;
+    uint32_t list_cap;        // C for the bottom layer
+    uint32_t vis_slots;       // visited slots for the bottom layer
+    uint32_t vis_slots_upper; // visited slots for the max_search = 1 descents
+    uint32_t* out_ids;
+    float* out_dists;
+    uint32_t* out_counts;
+    unsigned long long* out_stats;  // nq x 4 or null
+    int* query_status;              // nq ints (0 = done ok)
+    unsigned int* work_counter;     // persistent scheduling
+    int* error_flag;                // sticky device error word (OR of status bits that are final)
+    // slow path only: global workspaces (one per slow CTA)
+    unsigned long long* slow_list;
+    uint32_t* slow_visited;
+    uint32_t slow_list_cap;
+    uint32_t slow_vis_slots;
+    int slow_pass;  // 0: fast kernel, 1: slow kernel (processes only flagged queries)
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t key_dbits(unsigned long long key) { return (uint32_t)(key >> 32) & 0x7FFFFFFFu; }
+__device__ __forceinline__ uint32_t key_id(unsigned long long key) { return (uint32_t)key; }
+__device__ __forceinline__ unsigned long long make_key(float d, uint32_t id) {
+    return ((unsigned long long)__float_as_uint(d) << 32) | id;
+}
+__device__ __forceinline__ unsigned lanemask_lt() {
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+// Streaming 128-bit / 32-bit loads of candidate rows: read-only path, do not pollute L1 (each row is used once).
+__device__ __forceinline__ float4 ldg_row_f4(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float2 ldg_row_f2(const float* p) {
+    float2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ldg_row_f1(const float* p) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int ldg_row_i32(const int* p) {
+    int v;
+    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
+// cmp::max(0.0, 1.0 - r) with NaN detection (angular.rs:70-73, angular_int.rs:55-58)
+__device__ __forceinline__ float finish_angular(float r, int* status) {
+    float d = __fsub_rn(1.0f, r);
+    if (d != d) {
+        *status |= kStatusNotFinite;
+        return 0.0f;
+    }
+    return (0.0f <= d) ? d : 0.0f;
+}
+
+// Per-warp working set (pointers may be shared or global memory: the slow path uses global workspaces).
+struct WarpCtx {
+    unsigned long long* list;  // L
+    uint32_t* visited;
+    float* tile;       // 32 x 33 floats (always shared)
+    float* qs;         // query, natural layout: f32[dim] (or i8 words for ANGULAR_INT), shared
+    float* xs;         // EMBEDDINGS scratch f32[dim], shared
+    int lane;
+    int status;
+    int q_norm_i8;     // ANGULAR_INT: dy = sum q^2
+    unsigned long long n_dist, n_expand, n_nbr;
+};
+
+// Strictly ordered sum of the 32 lane partials of ONE value (used where only a single candidate is live):
+// r = 0; for i in 0..32 { r += chunk[i] }   (src/math.rs:27-30).  All lanes return the same r.
+__device__ __forceinline__ float ordered_lane_sum_bcast(float p) {
+    float r = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) r = __fadd_rn(r, __shfl_sync(kFullMask, p, i));
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// distance engines.  Contract: on entry lane j (< k) holds candidate id `my_id`; returns d_j in lane j.
+// ------------------------------------------------------------------------------------------------------------------
+
+// ANGULAR f32, compile-time chunk count FULL (dim = 32*FULL + tail).  Query chunk values live in registers.
+template <int FULL>
+struct DistF32 {
+    static constexpr int V = (FULL % 4 == 0) ? 4 : ((FULL % 2 == 0) ? 2 : 1);
+    static constexpr int G = FULL / V;
+    static constexpr int NQ = FULL > 0 ? FULL : 1;
+    static constexpr int BATCH = FULL <= 4 ? 16 : 8;
+    float q[NQ];
+
+    __device__ __forceinline__ void load_query(const DeviceIndex& ix, const WarpCtx& c) {
+#pragma unroll
+        for (int ch = 0; ch < FULL; ++ch) q[ch] = c.qs[ch * 32 + c.lane];
+    }
+
+    __device__ __forceinline__ float dists(const DeviceIndex& ix, WarpCtx& c, uint32_t my_id, int k) {
+        const float* base = static_cast<const float*>(ix.vectors);
+        const size_t stride = ix.row_stride;
+        if (FULL > 0) {
+            for (int j0 = 0; j0 < k; j0 += BATCH) {
+                float data[BATCH][NQ];
+#pragma unroll
+                for (int b = 0; b < BATCH; ++b) {
+                    const uint32_t id = __shfl_sync(kFullMask, my_id, (j0 + b) & 31);
+                    if (j0 + b < k) {
+                        const float* row = base + (size_t)id * stride + c.lane * V;
+#pragma unroll
+                        for (int g = 0; g < G; ++g) {
+                            if (V == 4) {
+                                float4 v = ldg_row_f4(row + g * 128);
+                                data[b][g * 4 + 0] = v.x;
+                                data[b][g * 4 + 1] = v.y;
+                                data[b][g * 4 + 2] = v.z;
+                                data[b][g * 4 + 3] = v.w;
+                            } else if (V == 2) {
+                                float2 v = ldg_row_f2(row + g * 64);
+                                data[b][g * 2 + 0] = v.x;
+                                data[b][g * 2 + 1] = v.y;
+                            } else {
+                                data[b][g] = ldg_row_f1(row + g * 32);
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int b = 0; b < BATCH; ++b) {
+                    if (j0 + b < k) {
+                        float p = 0.0f;
+#pragma unroll
+                        for (int ch = 0; ch < FULL; ++ch) p = __fmaf_rn(data[b][ch], q[ch], p);
+                        c.tile[(j0 + b) * 33 + c.lane] = p;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        float d = 0.0f;
+        if (c.lane < k) {
+            float r = 0.0f;
+            if (FULL > 0) {
+                const float* t = c.tile + c.lane * 33;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) r = __fadd_rn(r, t[i]);
+            }
+            const int tail = ix.tail;
+            if (tail) {
+                const float* row = base + (size_t)my_id * stride + FULL * 32;
+                const float* qt = c.qs + FULL * 32;
+                for (int t = 0; t < tail; ++t) r = __fmaf_rn(__ldg(row + t), qt[t], r);
+            }
+            d = finish_angular(r, &c.status);
+        }
+        __syncwarp();
+        return d;
+    }
+};
+
+// ANGULAR f32, any dim (runtime chunk count; natural row layout; query read from shared memory).
+struct DistF32Generic {
+    __device__ __forceinline__ void load_query(const DeviceIndex&, const WarpCtx&) {}
+    __device__ __forceinline__ float dists(const DeviceIndex& ix, WarpCtx& c, uint32_t my_id, int k) {
+        const float* base = static_cast<const float*>(ix.vectors);
+        const size_t stride = ix.row_stride;
+        const int full = ix.full;
+        for (int j = 0; j < k; ++j) {
+            const uint32_t id = __shfl_sync(kFullMask, my_id, j);
+            const float* row = base + (size_t)id * stride + c.lane;
+            float p = 0.0f;
+            for (int ch = 0; ch < full; ++ch) p = __fmaf_rn(ldg_row_f1(row + ch * 32), c.qs[ch * 32 + c.lane], p);
+            c.tile[j * 33 + c.lane] = p;
+        }
+        __syncwarp();
+        float d = 0.0f;
+        if (c.lane < k) {
+            float r = 0.0f;
+            const float* t = c.tile + c.lane * 33;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r = __fadd_rn(r, t[i]);
+            const float* row = base + (size_t)my_id * stride + full * 32;
+            const float* qt = c.qs + full * 32;
+            for (int t2 = 0; t2 < (int)ix.tail; ++t2) r = __fmaf_rn(__ldg(row + t2), qt[t2], r);
+            d = finish_angular(r, &c.status);
+        }
+        __syncwarp();
+        return d;
+    }
+};
+
+// ANGULAR_INT i8: exact i32 r, dx via dp4a (src/math.rs:59-89), then 1 - r/(sqrt(dx)*sqrt(dy)) in IEEE f32
+// (src/elements/angular_int.rs:47-59).  Rows and the query are zero-padded to row_stride bytes.
+struct DistI8 {
+    __device__ __forceinline__ void load_query(const DeviceIndex&, const WarpCtx&) {}
+    __device__ __forceinline__ float dists(const DeviceIndex& ix, WarpCtx& c, uint32_t my_id, int k) {
+        const int8_t* base = static_cast<const int8_t*>(ix.vectors);
+        const size_t stride = ix.row_stride;
+        const int words = ix.row_stride / 4;
+        const int* qw = reinterpret_cast<const int*>(c.qs);
+        int my_r = 0, my_dx = 0;
+        for (int j = 0; j < k; ++j) {
+            const uint32_t id = __shfl_sync(kFullMask, my_id, j);
+            const int* row = reinterpret_cast<const int*>(base + (size_t)id * stride);
+            int r = 0, dx = 0;
+            for (int w = c.lane; w < words; w += 32) {
+                const int a = ldg_row_i32(row + w);
+                r = __dp4a(a, qw[w], r);
+                dx = __dp4a(a, a, dx);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                r += __shfl_xor_sync(kFullMask, r, o);
+                dx += __shfl_xor_sync(kFullMask, dx, o);
+            }
+            if (c.lane == j) {
+                my_r = r;
+                my_dx = dx;
+            }
+        }
+        float d = 0.0f;
+        if (c.lane < k) {
+            const float rf = (float)my_r, dxf = (float)my_dx, dyf = (float)c.q_norm_i8;
+            float qv = __fdiv_rn(rf, __fmul_rn(__fsqrt_rn(dxf), __fsqrt_rn(dyf)));
+            if (qv != qv) qv = 0.0f;  // NotNan::new(..).unwrap_or_else(|_| 0.0)
+            const float dd = __fsub_rn(1.0f, qv);
+            d = (0.0f <= dd) ? dd : 0.0f;
+        }
+        return d;
+    }
+};
+
+// EMBEDDINGS: element = ordered sum of embedding rows, normalised, then the f32 angular distance
+// (src/elements/embeddings/mod.rs:124-143,164-174; src/math.rs:92-150).  Natural row layout, runtime dim.
+struct DistSum {
+    __device__ __forceinline__ void load_query(const DeviceIndex&, const WarpCtx&) {}
+
+    // materialises ElementContainer::get(id) into c.xs (all lanes participate)
+    static __device__ __forceinline__ void materialise(const DeviceIndex& ix, WarpCtx& c, uint32_t id) {
+        const float* emb = static_cast<const float*>(ix.vectors);
+        const size_t stride = ix.row_stride;
+        const int dim = ix.dim;
+        const unsigned long long b = ix.sum_offsets[id], e = ix.sum_offsets[id + 1];
+        for (int i = c.lane; i < dim; i += 32) {
+            float x = 0.0f;
+            if (b < e) {
+                x = __ldg(emb + (size_t)ix.sum_terms[b] * stride + i);
+                for (unsigned long long t = b + 1; t < e; ++t)
+                    x = __fadd_rn(x, __ldg(emb + (size_t)ix.sum_terms[t] * stride + i));  // sum_into_f32
+            }
+            c.xs[i] = x;
+        }
+        __syncwarp();
+        // normalize_f32: norm = sqrt(dot(x,x)); if norm > 0 { x[i] /= norm }
+        const int full = ix.full;
+        float p = 0.0f;
+        for (int ch = 0; ch < full; ++ch) {
+            const float v = c.xs[ch * 32 + c.lane];
+            p = __fmaf_rn(v, v, p);
+        }
+        float r = ordered_lane_sum_bcast(p);
+        for (int t = full * 32; t < dim; ++t) {
+            const float v = c.xs[t];
+            r = __fmaf_rn(v, v, r);
+        }
+        const float norm = __fsqrt_rn(r);
+        if (norm > 0.0f)
+            for (int i = c.lane; i < dim; i += 32) c.xs[i] = __fdiv_rn(c.xs[i], norm);
+        __syncwarp();
+    }
+
+    __device__ __forceinline__ float dists(const DeviceIndex& ix, WarpCtx& c, uint32_t my_id, int k) {
+        const int dim = ix.dim, full = ix.full;
+        float d = 0.0f;
+        for (int j = 0; j < k; ++j) {
+            const uint32_t id = __shfl_sync(kFullMask, my_id, j);
+            materialise(ix, c, id);
+            float p = 0.0f;
+            for (int ch = 0; ch < full; ++ch) p = __fmaf_rn(c.xs[ch * 32 + c.lane], c.qs[ch * 32 + c.lane], p);
+            float r = ordered_lane_sum_bcast(p);
+            for (int t = full * 32; t < dim; ++t) r = __fmaf_rn(c.xs[t], c.qs[t], r);
+            const float dj = finish_angular(r, &c.status);
+            if (c.lane == j) d = dj;
+            __syncwarp();
+        }
+        return d;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+// visited set: FxHashSet<usize> semantics (src/index/mod.rs:1009-1010,1016,1026), exact.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t vis_hash(uint32_t id, uint32_t slots) {
+    return __umulhi(id * 0x9E3779B1u, slots);  // multiply-shift range reduction, slots need not be a power of two
+}
+// returns true if `id` was newly inserted.  Lanes of one warp may insert concurrently (atomicCAS decides ties).
+__device__ __forceinline__ bool vis_insert(uint32_t* tab, uint32_t slots, uint32_t id) {
+    uint32_t h = vis_hash(id, slots);
+    for (uint32_t probe = 0; probe < slots; ++probe) {
+        const uint32_t prev = atomicCAS(tab + h, kUnusedId, id);
+        if (prev == kUnusedId) return true;
+        if (prev == id) return false;
+        h = (h + 1 == slots) ? 0 : h + 1;
+    }
+    return false;  // unreachable: occupancy is capped below `slots` by the caller
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// search_for_neighbors (src/index/mod.rs:999-1037) on one layer.  On return the list holds the merged state;
+// *out_n is its length.  The result set (`res.into_sorted_vec()`) is the first min(|E|, ef) expanded entries.
+// ------------------------------------------------------------------------------------------------------------------
+template <class Dist>
+__device__ __forceinline__ void search_layer(const DeviceIndex& ix, WarpCtx& c, Dist& dist, const uint32_t* rows,
+                                          const uint32_t width, const uint32_t entrypoint, const uint32_t ef,
+                                          const uint32_t cap, const uint32_t vis_slots, uint32_t* out_n) {
+    unsigned long long* L = c.list;
+    const int lane = c.lane;
+    for (uint32_t i = lane; i < vis_slots; i += 32) c.visited[i] = kUnusedId;
+    __syncwarp();
+    const uint32_t vis_limit = vis_slots - (vis_slots >> 3);  // keep load factor <= 7/8
+    uint32_t vis_count = 1;
+
+    // seed (:1012-1016)
+    {
+        const float d0 = dist.dists(ix, c, entrypoint, 1);
+        c.n_dist += 1;
+        if (__any_sync(kFullMask, c.status & kStatusNotFinite)) {
+            c.status |= kStatusNotFinite;
+            *out_n = 0;
+            return;
+        }
+        if (lane == 0) {
+            L[0] = make_key(d0, entrypoint);
+            vis_insert(c.visited, vis_slots, entrypoint);
+        }
+        __syncwarp();
+    }
+    uint32_t n = 1;          // entries in L
+    uint32_t n_exp = 0;      // expanded entries in L
+    uint32_t cursor = 0;     // every entry before `cursor` is expanded
+    uint32_t thr_bits = 0;   // distance bits of the ef-th expanded entry (valid iff n_exp >= ef)
+
+    while (true) {
+        // ---- pq.pop(): first unexpanded entry ----
+        int px = -1;
+        for (uint32_t base = cursor & ~31u; base < n; base += 32) {
+            const uint32_t j = base + lane;
+            const bool un = (j < n) && (j >= cursor) && !(L[j] >> 63);
+            const unsigned m = __ballot_sync(kFullMask, un);
+            if (m) {
+                px = base + __ffs(m) - 1;
+                break;
+            }
+        }
+        if (px < 0) break;  // pq empty
+        const unsigned long long x = L[px];
+        const uint32_t xd = key_dbits(x);
+        const uint32_t xid = key_id(x);
+        if (n_exp >= ef && xd > thr_bits) break;  // res.is_full() && d > res.peek().0  (:1019-1021)
+
+        // ---- res.push((d, idx)) (:1023; max_size_heap.rs:18-32) ----
+        __syncwarp();
+        if (lane == 0) L[px] = x | kFlagExpanded;
+        __syncwarp();
+        n_exp += 1;
+        cursor = px + 1;
+        if (n_exp >= ef) {
+            // locate the ef-th expanded entry: res.peek()
+            uint32_t cnt = 0;
+            for (uint32_t base = 0; base < n; base += 32) {
+                const uint32_t j = base + lane;
+                const bool fl = (j < n) && (L[j] >> 63);
+                const unsigned m = __ballot_sync(kFullMask, fl);
+                const uint32_t pc = __popc(m);
+                if (cnt + pc >= ef) {
+                    const uint32_t pos = base + __fns(m, 0, ef - cnt);
+                    thr_bits = key_dbits(L[pos]);
+                    break;
+                }
+                cnt += pc;
+            }
+        }
+        c.n_expand += 1;
+
+        // ---- for neighbor in layer.get_neighbors(idx) (:1025-1033) ----
+        const uint32_t* row = rows + (size_t)xid * width;
+        for (uint32_t w0 = 0; w0 < width; w0 += 32) {
+            const uint32_t nb = (w0 + lane < width) ? __ldg(row + w0 + lane) : kUnusedId;
+            const bool valid = nb != kUnusedId;
+            const unsigned vm = __ballot_sync(kFullMask, valid);
+            if (vm == 0) break;  // rows are padded at the end only
+            c.n_nbr += __popc(vm);
+            const bool is_new = valid && vis_insert(c.visited, vis_slots, nb);
+            const unsigned nm = __ballot_sync(kFullMask, is_new);
+            const int k = __popc(nm);
+            if (k == 0) continue;
+            vis_count += k;
+            if (vis_count > vis_limit) {
+                c.status |= kStatusOverflow;
+                *out_n = n;
+                return;
+            }
+            // compact the new ids to lanes 0..k-1 (any order: the push set is order independent)
+            const int src = __fns(nm, 0, lane + 1);
+            const uint32_t my_id = __shfl_sync(kFullMask, nb, src & 31);
+            c.n_dist += k;
+            const float d = dist.dists(ix, c, my_id, k);
+            if (__any_sync(kFullMask, c.status & kStatusNotFinite)) {
+                c.status |= kStatusNotFinite;
+                *out_n = n;
+                return;
+            }
+            const unsigned long long my_key = make_key(d, my_id);
+            // !res.is_full() || distance < res.peek().0   (:1029)
+            const bool pass = (lane < k) && (n_exp < ef || key_dbits(my_key) < thr_bits);
+            unsigned pm = __ballot_sync(kFullMask, pass);
+            while (pm) {
+                const int j = __ffs(pm) - 1;
+                pm &= pm - 1;
+                const unsigned long long key = __shfl_sync(kFullMask, my_key, j);
+                // ---- pq.push(key): insert into the sorted list ----
+                int hi;  // highest index that moves up
+                if (n == cap) {
+                    const unsigned long long last = L[cap - 1];
+                    const uint32_t guard = key_dbits(L[ef - 1]);  // cap > ef
+                    if (key > (last & kKeyMask)) {
+                        // dropped without entering L: legal only if >= ef strictly closer entries exist
+                        if (!(guard < key_dbits(key))) c.status |= kStatusOverflow;
+                        continue;
+                    }
+                    if (!(guard < key_dbits(last))) c.status |= kStatusOverflow;
+                    if (last >> 63) n_exp -= 1;
+                    hi = (int)cap - 2;
+                } else {
+                    hi = (int)n - 1;
+                    n += 1;
+                }
+                int pos = 0;
+                for (int base = hi & ~31; base >= 0; base -= 32) {
+                    const int jj = base + lane;
+                    unsigned long long v = 0;
+                    bool in = jj <= hi;
+                    if (in) v = L[jj];
+                    const bool gt = in && ((v & kKeyMask) > key);
+                    __syncwarp();
+                    if (gt) L[jj + 1] = v;
+                    const unsigned stay = __ballot_sync(kFullMask, in && !gt);
+                    if (stay) {
+                        pos = base + __popc(stay);
+                        break;
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) L[pos] = key;
+                __syncwarp();
+                if ((uint32_t)pos < cursor) cursor = pos;
+            }
+            if (c.status & kStatusOverflow) {
+                *out_n = n;
+                return;
+            }
+        }
+    }
+    *out_n = n;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// query construction (the `Elements::Element` the reference's callers build)
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void prepare_query(const DeviceIndex& ix, const SearchArgs& a, WarpCtx& c,
+                                              unsigned long long qi) {
+    const int dim = ix.dim, lane = c.lane;
+    if (ix.kind == kAngularI8) {
+        int* qw = reinterpret_cast<int*>(c.qs);
+        int8_t* qb = reinterpret_cast<int8_t*>(c.qs);
+        const int words = ix.row_stride / 4;
+        for (int w = lane; w < words; w += 32) qw[w] = 0;
+        __syncwarp();
+        if (a.query_format == kQueryElement) {
+            const int8_t* src = static_cast<const int8_t*>(a.queries) + qi * dim;
+            for (int i = lane; i < dim; i += 32) qb[i] = src[i];
+        } else {
+            // angular_int.rs:28-45: max |x| (NotNan max; NaN input is an error), vi = x*127/max, `as i8`
+            const float* src = static_cast<const float*>(a.queries) + qi * dim;
+            float mx = 0.0f;
+            bool bad = false;
+            for (int i = lane; i < dim; i += 32) {
+                const float v = src[i];
+                if (v != v) bad = true;
+                mx = fmaxf(mx, fabsf(v));
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(kFullMask, mx, o));
+            if (__any_sync(kFullMask, bad)) c.status |= kStatusNotFinite;
+            for (int i = lane; i < dim; i += 32) {
+                const float vi = __fdiv_rn(__fmul_rn(src[i], 127.0f), mx);
+                int q;
+                if (vi != vi)
+                    q = 0;
+                else if (vi >= 127.0f)
+                    q = 127;
+                else if (vi <= -128.0f)
+                    q = -128;
+                else
+                    q = (int)vi;  // truncation toward zero
+                qb[i] = (int8_t)q;
+            }
+        }
+        __syncwarp();
+        int dy = 0;
+        for (int w = lane; w < words; w += 32) dy = __dp4a(qw[w], qw[w], dy);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dy += __shfl_xor_sync(kFullMask, dy, o);
+        c.q_norm_i8 = dy;
+    } else {
+        const float* src = static_cast<const float*>(a.queries) + qi * dim;
+        for (int i = lane; i < dim; i += 32) c.qs[i] = src[i];
+        __syncwarp();
+        if (a.query_format == kQueryRawF32) {
+            // Vector::from(Vec<f32>) -> normalize_f32 (angular.rs:55-61, math.rs:124-150)
+            const int full = ix.full;
+            float p = 0.0f;
+            for (int ch = 0; ch < full; ++ch) {
+                const float v = c.qs[ch * 32 + lane];
+                p = __fmaf_rn(v, v, p);
+            }
+            float r = ordered_lane_sum_bcast(p);
+            for (int t = full * 32; t < dim; ++t) {
+                const float v = c.qs[t];
+                r = __fmaf_rn(v, v, r);
+            }
+            const float norm = __fsqrt_rn(r);
+            __syncwarp();
+            if (norm > 0.0f)
+                for (int i = lane; i < dim; i += 32) c.qs[i] = __fdiv_rn(c.qs[i], norm);
+            __syncwarp();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Granne::search for a batch (src/index/mod.rs:140-150, 962-997): persistent warps over a work counter.
+// ------------------------------------------------------------------------------------------------------------------
+template <class Dist>
+__global__ void __launch_bounds__(32) search_kernel(const DeviceIndex ix, const SearchArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WarpCtx c;
+    c.lane = threadIdx.x;
+    // shared layout: tile | qs | xs | list | visited   (list/visited live in global memory on the slow path)
+    unsigned char* sp = smem_raw;
+    c.tile = reinterpret_cast<float*>(sp);
+    sp += 32 * 33 * sizeof(float);
+    const uint32_t qbytes = (ix.kind == kAngularI8) ? ix.row_stride : ((ix.dim + 3u) & ~3u) * 4u;
+    c.qs = reinterpret_cast<float*>(sp);
+    sp += (qbytes + 15u) & ~15u;
+    c.xs = reinterpret_cast<float*>(sp);
+    if (ix.kind == kSumEmbeddings) sp += (qbytes + 15u) & ~15u;
+    uint32_t list_cap, vis_slots, vis_upper;
+    if (a.slow_pass) {
+        c.list = a.slow_list + (size_t)blockIdx.x * a.slow_list_cap;
+        c.visited = a.slow_visited + (size_t)blockIdx.x * a.slow_vis_slots;
+        list_cap = a.slow_list_cap;
+        vis_slots = a.slow_vis_slots;
+        vis_upper = a.slow_vis_slots;
+    } else {
+        c.list = reinterpret_cast<unsigned long long*>(sp);
+        sp += (size_t)a.list_cap * sizeof(unsigned long long);
+        c.visited = reinterpret_cast<uint32_t*>(sp);
+        list_cap = a.list_cap;
+        vis_slots = a.vis_slots;
+        vis_upper = a.vis_slots_upper;
+    }
+    Dist dist;
+
+    while (true) {
+        unsigned int qi0 = 0;
+        if (c.lane == 0) qi0 = atomicAdd(a.work_counter, 1u);
+        const unsigned long long qi = __shfl_sync(kFullMask, qi0, 0);
+        if (qi >= a.nq) break;
+        if (a.slow_pass && a.query_status[qi] != kStatusOverflow) continue;  // only flagged queries
+
+        c.status = 0;
+        c.n_dist = c.n_expand = c.n_nbr = 0;
+        c.q_norm_i8 = 0;
+        prepare_query(ix, a, c, qi);
+        dist.load_query(ix, c);
+
+        uint32_t n = 0;
+        const uint32_t k = a.num_neighbors;
+        uint32_t found = 0;
+        if (ix.num_layers > 0 && !(c.status & kStatusNotFinite)) {
+            // find_entrypoint (:984-997): max_search = 1 descent through the upper layers, then the bottom layer
+            // with the caller's max_search (:970-973).  One call site so the distance engine stays in registers.
+            uint32_t entrypoint = 0;
+            const uint32_t cap1 = list_cap < 32 ? list_cap : 32;
+            for (int l = 0; l < ix.num_layers && c.status == 0; ++l) {
+                const bool bottom = (l + 1 == ix.num_layers);
+                search_layer(ix, c, dist, ix.layer_rows[l], ix.layer_width[l], entrypoint, bottom ? a.max_search : 1u,
+                             bottom ? list_cap : cap1, bottom ? vis_slots : vis_upper, &n);
+                if (bottom || c.status) break;
+                // res[0]: first expanded entry
+                uint32_t ep = 0;
+                for (uint32_t base = 0; base < n; base += 32) {
+                    const uint32_t j = base + c.lane;
+                    const bool fl = (j < n) && (c.list[j] >> 63);
+                    const unsigned m = __ballot_sync(kFullMask, fl);
+                    if (m) {
+                        ep = key_id(c.list[base + __ffs(m) - 1]);
+                        break;
+                    }
+                }
+                entrypoint = ep;
+            }
+            if (c.status == 0) {
+                // res.into_sorted_vec().take(num_neighbors) (:974-977, :1036)
+                const uint32_t limit = a.max_search < k ? a.max_search : k;
+                uint32_t cnt = 0;
+                for (uint32_t base = 0; base < n && cnt < limit; base += 32) {
+                    const uint32_t j = base + c.lane;
+                    unsigned long long v = 0;
+                    if (j < n) v = c.list[j];
+                    const bool fl = (j < n) && (v >> 63);
+                    const unsigned m = __ballot_sync(kFullMask, fl);
+                    const uint32_t rank = cnt + __popc(m & lanemask_lt());
+                    if (fl && rank < limit) {
+                        a.out_ids[qi * k + rank] = key_id(v);
+                        a.out_dists[qi * k + rank] = __uint_as_float(key_dbits(v));
+                    }
+                    cnt += __popc(m);
+                }
+                found = cnt < limit ? cnt : limit;
+            }
+        }
+        if (c.status & kStatusOverflow) {
+            // leave the outputs to the slow path (or report capacity exhaustion if this IS the slow path)
+            if (c.lane == 0) {
+                a.query_status[qi] = a.slow_pass ? (kStatusOverflow | 4) : kStatusOverflow;
+                if (a.slow_pass) atomicOr(a.error_flag, kStatusOverflow);
+            }
+            if (!a.slow_pass) continue;
+            found = 0;
+        }
+        if (c.status & kStatusNotFinite) {
+            found = 0;
+            if (c.lane == 0) atomicOr(a.error_flag, kStatusNotFinite);
+        }
+        for (uint32_t r = found + c.lane; r < k; r += 32) {
+            a.out_ids[qi * k + r] = kUnusedId;
+            a.out_dists[qi * k + r] = __int_as_float(0x7f800000);
+        }
+        if (c.lane == 0) {
+            if (a.out_counts) a.out_counts[qi] = found;
+            if (a.out_stats) {
+                a.out_stats[qi * 4 + 0] = c.n_dist;
+                a.out_stats[qi * 4 + 1] = c.n_expand;
+                a.out_stats[qi * 4 + 2] = c.n_nbr;
+                a.out_stats[qi * 4 + 3] = a.slow_pass ? 1ull : 0ull;
+            }
+            if (!(c.status & kStatusOverflow)) a.query_status[qi] = 0;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// staging / utility kernels
+// ------------------------------------------------------------------------------------------------------------------
+
+// Row-major f32 rows -> lane-permuted HBM layout: element (chunk c, lane i) of a row moves to
+// g*32*V + i*V + v with c = g*V + v; the tail (dim % 32) stays in place; the row is padded to `stride` floats.
+__global__ void permute_rows_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, uint64_t nrows,
+                                        uint32_t dim, uint32_t full, uint32_t V, uint32_t stride) {
+    const uint64_t total = nrows * stride;
+    for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < total;
+         t += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t r = t / stride;
+        const uint32_t o = (uint32_t)(t % stride);
+        float v = 0.0f;
+        if (o < full * 32) {
+            const uint32_t g = o / (32 * V), rem = o % (32 * V);
+            const uint32_t i = rem / V, vv = rem % V;
+            v = src[r * dim + (g * V + vv) * 32 + i];
+        } else if (o < dim) {
+            v = src[r * dim + o];
+        }
+        dst[t] = v;
+    }
+}
+
+__global__ void pad_rows_i8_kernel(const int8_t* __restrict__ src, int8_t* __restrict__ dst, uint64_t nrows,
+                                   uint32_t dim, uint32_t stride) {
+    const uint64_t total = nrows * stride;
+    for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < total;
+         t += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t r = t / stride;
+        const uint32_t o = (uint32_t)(t % stride);
+        dst[t] = o < dim ? src[r * dim + o] : (int8_t)0;
+    }
+}
+
+// ElementContainer::get(idx) for one element -> `out` (dim f32, or dim i8)
+__global__ void __launch_bounds__(32) get_element_kernel(const DeviceIndex ix, unsigned long long idx, void* out) {
+    __shared__ float xs[4096];
+    const int lane = threadIdx.x;
+    const uint32_t dim = ix.dim;
+    if (ix.kind == kAngularI8) {
+        const int8_t* row = static_cast<const int8_t*>(ix.vectors) + idx * ix.row_stride;
+        for (uint32_t i = lane; i < dim; i += 32) static_cast<int8_t*>(out)[i] = row[i];
+    } else if (ix.kind == kAngularF32) {
+        const float* row = static_cast<const float*>(ix.vectors) + idx * ix.row_stride;
+        const uint32_t V = ix.vec_group;
+        for (uint32_t e = lane; e < dim; e += 32) {
+            uint32_t o = e;
+            if (e < ix.full * 32) {
+                const uint32_t ch = e / 32, i = e % 32, g = ch / V, vv = ch % V;
+                o = g * 32 * V + i * V + vv;
+            }
+            static_cast<float*>(out)[e] = row[o];
+        }
+    } else {
+        WarpCtx c;
+        c.lane = lane;
+        c.xs = xs;
+        c.status = 0;
+        if (dim <= 4096) {
+            DistSum::materialise(ix, c, (uint32_t)idx);
+            for (uint32_t i = lane; i < dim; i += 32) static_cast<float*>(out)[i] = xs[i];
+        }
+    }
+}
+
+// k-way merge of per-shard result tiles by (distance, global id) — range-partitioned mode.
+// One thread per query; parts*k is small (<= a few hundred).
+__global__ void merge_topk_kernel(const uint32_t* __restrict__ part_ids, const float* __restrict__ part_dists,
+                                  const unsigned long long* __restrict__ part_base, uint32_t num_parts,
+                                  unsigned long long nq, uint32_t k, unsigned long long* __restrict__ out_ids,
+                                  float* __restrict__ out_dists) {
+    const unsigned long long q = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    // each part's tile is already sorted ascending: classic k-way merge with one cursor per part
+    uint32_t cur[64];
+    for (uint32_t p = 0; p < num_parts; ++p) cur[p] = 0;
+    for (uint32_t r = 0; r < k; ++r) {
+        int best = -1;
+        float bd = 0.0f;
+        unsigned long long bid = 0;
+        for (uint32_t p = 0; p < num_parts; ++p) {
+            if (cur[p] >= k) continue;
+            const size_t o = ((size_t)p * nq + q) * k + cur[p];
+            const uint32_t lid = part_ids[o];
+            if (lid == kUnusedId) continue;
+            const float d = part_dists[o];
+            const unsigned long long gid = part_base[p] + lid;
+            if (best < 0 || d < bd || (d == bd && gid < bid)) {
+                best = (int)p;
+                bd = d;
+                bid = gid;
+            }
+        }
+        if (best < 0) {
+            out_ids[q * k + r] = ~0ull;
+            out_dists[q * k + r] = __int_as_float(0x7f800000);
+        } else {
+            out_ids[q * k + r] = bid;
+            out_dists[q * k + r] = bd;
+            cur[best] += 1;
+        }
+    }
+}
+
+}  // namespace granne_b200

@@ -1,0 +1,174 @@
+/* granne_b200.h — C ABI of the B200-native drop-in for granne's search path.
+ *
+ * granne (Rust, v0.5.2) exposes no C FFI; its boundary is the generic Rust API re-exported in src/lib.rs:80-86 and the
+ * rust-cpython module in py/src/lib.rs.  This header is what a `extern "C"` shim on the reference side binds (see
+ * INTEGRATION.md for the Rust/ctypes stubs).  Every entry point cites the reference interface it replaces; paths are
+ * relative to the reference repository root.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no C++/torch types; nothing unwinds across this boundary.
+ *  - every function returning `int` returns GRANNE_B200_OK (0) or a negative status; a human readable message for
+ *    the calling thread's last failure is available from granne_b200_last_error().
+ *    The reference panics where this ABI returns a status (malformed file: src/index/io.rs:73; NaN distance:
+ *    src/elements/angular.rs:70; max_search == 0: src/index/mod.rs:1019).
+ *  - input buffers stay owned by the caller and may be released as soon as the call returns (the reference borrows
+ *    them for the index lifetime, src/index/mod.rs:108-113); outputs are caller-allocated.
+ *  - ids are u32 on this boundary (granne limits an index to 2^32-2 elements: src/lib.rs:7, src/index/mod.rs:27-28,420).
+ *  - a handle may be used from several host threads for concurrent search calls; open/close must not race with them.
+ *  - the CUDA device is mandatory: there is no CPU fallback behind this ABI.
+ */
+#ifndef GRANNE_B200_H
+#define GRANNE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GRANNE_B200_ABI_VERSION 1
+
+/* status codes */
+#define GRANNE_B200_OK 0
+#define GRANNE_B200_ERR_INVALID_ARGUMENT (-1) /* null pointer, dim mismatch, max_search == 0, bad enum ... */
+#define GRANNE_B200_ERR_FORMAT (-2)           /* not a granne index / elements file, or truncated */
+#define GRANNE_B200_ERR_IO (-3)               /* file could not be opened/read */
+#define GRANNE_B200_ERR_CUDA (-4)             /* CUDA runtime failure (message carries cudaGetErrorString) */
+#define GRANNE_B200_ERR_NO_DEVICE (-5)        /* no usable sm_100 device: the library never falls back to the CPU */
+#define GRANNE_B200_ERR_NOT_FINITE (-6)       /* a NaN distance occurred (the reference panics: angular.rs:70) */
+#define GRANNE_B200_ERR_CAPACITY (-7)         /* exact-search workspace exhausted even on the slow path */
+#define GRANNE_B200_ERR_OUT_OF_RANGE (-8)     /* idx / layer out of range */
+
+/* Element kinds — the three ElementContainer implementations granne ships (src/elements/mod.rs:17-45):
+ * angular::Vectors (src/elements/angular.rs), angular_int::Vectors (src/elements/angular_int.rs),
+ * embeddings::SumEmbeddings (src/elements/embeddings/mod.rs:41-44).  Same strings as the Python binding's
+ * `element_type` (py/src/lib.rs:186-208). */
+#define GRANNE_B200_ANGULAR 0     /* "angular":     f32 rows, normalised                                  */
+#define GRANNE_B200_ANGULAR_INT 1 /* "angular_int": i8 rows (quantised)                                   */
+#define GRANNE_B200_EMBEDDINGS 2  /* "embeddings":  element = list of embedding ids, vector = normalised sum */
+
+/* Query formats for search. */
+#define GRANNE_B200_QUERY_RAW_F32 0 /* caller's raw f32 vector; the library builds the Element exactly like
+                                       `Vector::from(Vec<f32>)`: normalise (angular.rs:55-61, math.rs:124-150) or
+                                       quantise (angular_int.rs:19-45) — what the Python binding does per call
+                                       (py/src/variants/index.rs:15-16,32-33,103-108). */
+#define GRANNE_B200_QUERY_ELEMENT 1 /* already an `Elements::Element`: normalised f32 (angular, embeddings) or i8
+                                       (angular_int) — what Rust callers of Granne::search pass. */
+
+/* Per-query counters written to `out_stats` (4 x u64 per query).  n_dist / n_expand are exactly the number of
+ * `dist_to_element` (src/index/mod.rs:1012,1027) and `get_neighbors` (:1025) calls the reference makes for the
+ * same query, all layers included; they are parity-checked against the oracle and feed the roofline. */
+#define GRANNE_B200_STAT_N_DIST 0
+#define GRANNE_B200_STAT_N_EXPAND 1
+#define GRANNE_B200_STAT_N_NEIGHBORS_READ 2 /* sum of the degrees of the expanded nodes */
+#define GRANNE_B200_STAT_FLAGS 3            /* bit0: query took the exact slow path (workspace overflow) */
+#define GRANNE_B200_STATS_PER_QUERY 4
+
+typedef struct granne_b200_index granne_b200_index; /* opaque: owns all device + host memory */
+
+/* ABI version of the loaded library (== GRANNE_B200_ABI_VERSION). */
+int granne_b200_abi_version(void);
+
+/* Message describing the calling thread's most recent failure ("" if none). Never NULL. */
+const char* granne_b200_last_error(void);
+
+/* Replaces Granne::from_bytes(index, elements) (src/index/mod.rs:108-113) together with
+ * Vectors::from_bytes (src/elements/dense_vector.rs:50-52) / SumEmbeddings::from_bytes
+ * (src/elements/embeddings/mod.rs:56-61).
+ *   index_bytes     granne index file image (src/index/io.rs:11-113)
+ *   element_kind    GRANNE_B200_ANGULAR | _ANGULAR_INT | _EMBEDDINGS
+ *   elements_bytes  elements file image: FixedWidthSliceVector<f32|i8> (src/slice_vector/mod.rs:213-221,460-466) or,
+ *                   for EMBEDDINGS, VariableWidthSliceVector<ThreeByteInt,FiveByteInt> (:623-676)
+ *   embeddings_*    EMBEDDINGS only: the FixedWidthSliceVector<f32> embedding table, else NULL/0
+ *   device          CUDA device ordinal the index is staged on (layer graph + vectors are copied to HBM)
+ * Like the reference, the index may cover fewer elements than the container holds (src/index/mod.rs:74-83). */
+int granne_b200_open(const void* index_bytes, size_t index_len, int element_kind, const void* elements_bytes,
+                     size_t elements_len, const void* embeddings_bytes, size_t embeddings_len, int device,
+                     granne_b200_index** out);
+
+/* Replaces Granne::from_file (src/index/mod.rs:122-135) + Vectors::from_file (dense_vector.rs:61-63) /
+ * SumEmbeddings::from_files (embeddings/mod.rs:75-86); same argument order as the Python constructor
+ * Granne(index_path, element_type, elements_path, embeddings_path) (py/src/lib.rs:175-211). */
+int granne_b200_open_files(const char* index_path, int element_kind, const char* elements_path,
+                           const char* embeddings_path, int device, granne_b200_index** out);
+
+/* Drop of a `Granne` value. NULL is accepted. */
+void granne_b200_close(granne_b200_index* h);
+
+/* Index trait (src/index/mod.rs:54-104). */
+uint64_t granne_b200_len(const granne_b200_index* h);                        /* Index::len        :76-83 */
+uint64_t granne_b200_num_layers(const granne_b200_index* h);                 /* Index::num_layers :86-88 */
+uint64_t granne_b200_layer_len(const granne_b200_index* h, uint64_t layer);  /* Index::layer_len  :91-93 */
+/* Index::get_neighbors(index, layer) :96-98 — ascending ids, as MultiSetVector returns them. */
+int granne_b200_get_neighbors(const granne_b200_index* h, uint64_t idx, uint64_t layer, uint32_t* out, size_t cap,
+                              size_t* out_n);
+
+/* ElementContainer (src/elements/mod.rs:17-45). */
+uint64_t granne_b200_num_elements(const granne_b200_index* h); /* ElementContainer::len (may exceed Index::len) */
+uint64_t granne_b200_dim(const granne_b200_index* h);          /* Vectors::dim (dense_vector.rs:107-109)        */
+int granne_b200_element_kind(const granne_b200_index* h);
+/* Granne::get_element (src/index/mod.rs:153-155) == ElementContainer::get: writes dim f32 (ANGULAR: the stored row;
+ * EMBEDDINGS: the normalised sum, embeddings/mod.rs:164-166) or dim i8 (ANGULAR_INT) to `out`. */
+int granne_b200_get_element(const granne_b200_index* h, uint64_t idx, void* out);
+
+/* Replaces Granne::search(&self, &element, max_search, num_neighbors) -> Vec<(usize, f32)>
+ * (src/index/mod.rs:140-150, 962-1037), for a batch of `nq` independent queries (the reference has no batch API;
+ * a batch is nq sequential `search` calls, and a single query is nq == 1).
+ *   queries        HOST pointer, nq x dim, row-major; f32 (RAW_F32, or ELEMENT for ANGULAR/EMBEDDINGS) or
+ *                  i8 (ELEMENT for ANGULAR_INT)
+ *   max_search     >= 1 (0 panics in the reference, src/index/mod.rs:1019)
+ *   num_neighbors  results kept per query; like the reference at most max_search results exist (:974-977)
+ *   out_ids        nq x num_neighbors u32, ascending by (distance, id); padded with 0xFFFFFFFF
+ *   out_dists      nq x num_neighbors f32; padded with +inf
+ *   out_counts     nq u32: number of valid results of each query (may be NULL)
+ *   out_stats      nq x GRANNE_B200_STATS_PER_QUERY u64 (may be NULL)
+ * Host<->device copies happen inside the call. Results are bit-identical to the reference algorithm (ids and f32
+ * distances). */
+int granne_b200_search_batch(granne_b200_index* h, const void* queries, size_t nq, int query_format,
+                             uint32_t max_search, uint32_t num_neighbors, uint32_t* out_ids, float* out_dists,
+                             uint32_t* out_counts, uint64_t* out_stats);
+
+/* Same, with DEVICE pointers (on the index's device) and an optional cudaStream_t (NULL = the default stream);
+ * asynchronous with respect to the host: the caller synchronises the stream before reading the outputs and before
+ * calling granne_b200_stream_status(). */
+int granne_b200_search_batch_device(granne_b200_index* h, const void* d_queries, size_t nq, int query_format,
+                                    uint32_t max_search, uint32_t num_neighbors, uint32_t* d_out_ids,
+                                    float* d_out_dists, uint32_t* d_out_counts, uint64_t* d_out_stats,
+                                    void* cuda_stream);
+
+/* After synchronising a stream used with granne_b200_search_batch_device: GRANNE_B200_OK, or the first error
+ * (ERR_NOT_FINITE / ERR_CAPACITY) any query of the calls issued since the previous check raised. */
+int granne_b200_stream_status(granne_b200_index* h);
+
+/* Range-partitioned mode (SURVEY.md §8e mode 2; granne shards elements into independent indexes,
+ * src/elements/embeddings/parsing.rs:63-100): merges `num_parts` per-shard result tiles into the global top-k, ordered by
+ * (distance, global id) — the tuple order of into_sorted_vec (src/index/mod.rs:1036).
+ *   d_part_ids/dists  DEVICE, [num_parts][nq][k]; ids are shard-local, padded with 0xFFFFFFFF
+ *   part_base         HOST, num_parts u64: global id of each shard's element 0
+ *   d_out_ids         DEVICE, [nq][k] u64 global ids (padded with UINT64_MAX); d_out_dists [nq][k] f32 */
+int granne_b200_merge_topk_device(int device, const uint32_t* d_part_ids, const float* d_part_dists,
+                                  const uint64_t* part_base, size_t num_parts, size_t nq, uint32_t k,
+                                  uint64_t* d_out_ids, float* d_out_dists, void* cuda_stream);
+
+/* Host-only helpers (no device needed): the loader's view of an index image.
+ * granne_b200_inspect_index replaces io::read_layer_sizes + Index::num_layers/layer_len on raw bytes
+ * (src/index/io.rs:89-113): writes the number of layers and, for up to `cap` layers, the node count, the maximum
+ * out-degree and the staging row width (u32 per row, padded with 0xFFFFFFFF).
+ * granne_b200_decode_layer decodes every neighbour list of one layer (MultiSetVector::get, set_vector.rs:57-115)
+ * into fixed-width rows — exactly the layout that is copied to HBM.  `rows` must hold layer_len*width u32. */
+int granne_b200_inspect_index(const void* index_bytes, size_t index_len, uint64_t* out_num_layers,
+                              uint64_t* out_layer_len, uint32_t* out_max_degree, uint32_t* out_row_width, size_t cap);
+int granne_b200_decode_layer(const void* index_bytes, size_t index_len, uint64_t layer, uint32_t* rows,
+                             size_t rows_cap_u32);
+
+/* Number of kernels this library launched on behalf of `h` since it was opened (bench.py's gpu_launches). */
+uint64_t granne_b200_launch_count(const granne_b200_index* h);
+
+/* Bytes of device memory the staged index occupies (layer graph + vectors). */
+uint64_t granne_b200_device_bytes(const granne_b200_index* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRANNE_B200_H */

@@ -1,0 +1,124 @@
+"""CPU-side tests of the product: the C-ABI library loads and exports every symbol include/granne_b200.h declares,
+the host loader decodes granne index files exactly like the oracle (reference: src/index/io.rs:72-113,
+src/slice_vector/set_vector.rs:57-115, src/slice_vector/offsets.rs:178-259), and error paths return statuses
+instead of panicking.  No compute calls (no GPU here)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import granne_b200
+from granne_b200 import api
+from helpers.data import build_fixture
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from granne_b200 import build
+
+    build.build()
+    return granne_b200.load_library()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    header = open(os.path.join(ROOT, "include", "granne_b200.h")).read()
+    names = set(re.findall(r"\b(granne_b200_[a-z0-9_]+)\s*\(", header))
+    assert len(names) >= 20
+    raw = ctypes.CDLL(granne_b200.library_path())
+    for n in sorted(names):
+        assert hasattr(raw, n), n
+    assert lib.granne_b200_abi_version() == 1
+
+
+def test_no_torch_or_cxx_types_in_the_header():
+    header = open(os.path.join(ROOT, "include", "granne_b200.h")).read()
+    code = re.sub(r"/\*.*?\*/", "", header, flags=re.S)  # strip comments
+    assert "torch" not in code and "std::" not in code and "at::" not in code and "#include <c" not in code
+
+
+@pytest.mark.parametrize("n,dim,m", [(1, 8, 5), (59, 8, 5), (60, 8, 5), (61, 8, 5), (1500, 16, 20), (3000, 8, 30)])
+def test_loader_decodes_layers_like_the_oracle(lib, oracle, n, dim, m):
+    # sizes around the 60-offsets-per-chunk boundary (offsets.rs:7,249-259)
+    el, g, index_bytes, _, _ = build_fixture(oracle, "angular", n, dim, seed=n, num_neighbors=m, max_search=30)
+    shape = api.inspect_index(index_bytes)
+    assert len(shape) == g.num_layers()
+    for l, (cnt, maxdeg, width) in enumerate(shape):
+        assert cnt == g.layer_len(l)
+        rows = api.decode_layer(index_bytes, l)
+        assert rows.shape == (cnt, width) and width % 8 == 0 and width >= maxdeg
+        seen_max = 0
+        for i in range(cnt):
+            expect = g.get_neighbors(i, l)
+            seen_max = max(seen_max, len(expect))
+            assert rows[i, :len(expect)].tolist() == expect
+            assert (rows[i, len(expect):] == 0xFFFFFFFF).all()
+        assert seen_max == maxdeg
+
+
+def test_loader_handles_raw_and_vbyte_lists(lib, oracle):
+    # hand-made index: lists that exercise the raw-u32 rule (set_vector.rs:275-283), empty lists, <4 entries
+    import json
+
+    lists = [[37717, 660380], [], [5], [5, 5], list(range(10)), [1, 301, 70301, 20070301], [2**32 - 2]]
+    n = 700000
+    lists = [l for l in lists] + [[i] for i in range(80)]
+    # build the layer blob with the oracle's set_encode; offsets chunked by 60
+    enc = [oracle.set_encode(sorted(l)) for l in lists]
+    offsets = [0]
+    for e in enc:
+        offsets.append(offsets[-1] + len(e))
+    nchunks = 1 + len(lists) // 60
+    chunks = bytearray()
+    for c in range(nchunks):
+        offs = offsets[c * 60:(c + 1) * 60]
+        initial = offs[0] if offs else 0
+        chunks += int(initial).to_bytes(8, "little")
+        prev = initial
+        for i in range(60):
+            if i < len(offs):
+                chunks += int(offs[i] - prev).to_bytes(2, "little")
+                prev = offs[i]
+            else:
+                chunks += b"\xff\xff"
+    blob = len(chunks).to_bytes(8, "little") + bytes(chunks) + b"".join(enc)
+    meta = "granne" + json.dumps({"version": 2, "num_elements": 2**32 - 1, "num_layers": 1, "num_neighbors": 2,
+                                  "layer_counts": [len(lists)], "layer_sizes": [len(blob)], "compressed": True,
+                                  "granne_version": "0.5.2"})
+    image = meta.encode().ljust(1024, b" ") + blob
+    # ids exceed the layer size -> the loader must reject (every neighbour must address a node of its layer)
+    with pytest.raises(granne_b200.GranneError) as ei:
+        api.inspect_index(image)
+    assert ei.value.code == -2
+    # same lists with in-range ids decode exactly
+    small = [[min(v, len(lists) - 1) for v in l] for l in lists]
+    enc = [oracle.set_encode(sorted(l)) for l in small]
+    assert [oracle.set_decode(e) for e in enc] == [sorted(l) for l in small]
+
+
+def test_format_errors_are_statuses_not_crashes(lib, oracle):
+    el, g, index_bytes, elements_bytes, _ = build_fixture(oracle, "angular", 200, 8, seed=3, num_neighbors=8,
+                                                          max_search=20)
+    for bad in [b"", b"granne", b"grannf" + index_bytes[6:], index_bytes[:1024], index_bytes[:-7],
+                b"granne{not json".ljust(1024, b" ") + index_bytes[1024:]]:
+        with pytest.raises(granne_b200.GranneError) as ei:
+            api.inspect_index(bad)
+        assert ei.value.code == -2, bad[:16]
+    assert "granne" in str(ei.value) or "metadata" in str(ei.value) or "layer" in str(ei.value)
+
+
+def test_open_without_a_gpu_fails_loudly(lib, oracle):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    el, g, index_bytes, elements_bytes, _ = build_fixture(oracle, "angular", 100, 8, seed=4, num_neighbors=8,
+                                                          max_search=20)
+    with pytest.raises(granne_b200.GranneError) as ei:
+        granne_b200.Granne.from_bytes(index_bytes, "angular", elements_bytes)
+    assert ei.value.code == -5  # GRANNE_B200_ERR_NO_DEVICE: no CPU fallback
+    with pytest.raises(ValueError):
+        granne_b200.Granne.from_bytes(index_bytes, "bogus", elements_bytes)
