@@ -270,7 +270,7 @@ LaunchPlan make_plan(const Handle* h, uint32_t max_search) {
     uint64_t want = std::max<uint64_t>(1024, (uint64_t)max_search * std::min<uint32_t>(deg, 64));
     want = (want + 31) & ~31ull;
     const uint32_t qbytes = (d.kind == gb::kAngularI8) ? d.row_stride : ((d.dim + 3u) & ~3u) * 4u;
-    const size_t fixed = 32 * 33 * 4 + ((qbytes + 15u) & ~15u) * (d.kind == gb::kSumEmbeddings ? 2 : 1) +
+    const size_t fixed = gb::kTileBytes + ((qbytes + 15u) & ~15u) * (d.kind == gb::kSumEmbeddings ? 2 : 1) +
                          (size_t)p.list_cap * 8;
     const size_t budget = h->smem_optin;
     if (fixed + 4096 > budget) {  // caller rejects: the candidate list alone does not fit

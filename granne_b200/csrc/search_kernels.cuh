@@ -7,7 +7,7 @@
 //   * a sorted candidate list L (capacity C = max_search + slack) that merges the reference's two heaps:
 //     `res` (bounded max-heap of expanded nodes) and `pq` (unbounded min-heap frontier) — see "Exactness" below,
 //   * an exact visited set (open-addressing hash of u32 ids; the reference's FxHashSet),
-//   * a 32x33 f32 tile used to reproduce the reference's strictly ordered 32-lane partial-sum reduction.
+//   * a 32x36 f32 tile used to reproduce the reference's strictly ordered 32-lane partial-sum reduction.
 // Candidate vectors are gathered straight from HBM with fully coalesced 128-bit loads (the row layout in HBM is
 // lane-permuted so that one LDG.128 per lane fetches a whole 512-byte row), all rows of one expansion in flight at once.
 //
@@ -35,6 +35,8 @@ constexpr uint32_t kUnusedId = 0xFFFFFFFFu;
 constexpr unsigned long long kFlagExpanded = 1ull << 63;
 constexpr unsigned long long kKeyMask = ~kFlagExpanded;
 constexpr unsigned kFullMask = 0xFFFFFFFFu;
+constexpr int kTileStride = 36;  // floats per tile row: 16-byte aligned rows, conflict-free LDS.128 per quarter warp
+constexpr int kTileBytes = 32 * kTileStride * 4 + 128;  // tile + 32 x u32 id scratch
 
 enum ElementKind : int { kAngularF32 = 0, kAngularI8 = 1, kSumEmbeddings = 2 };
 enum QueryFormat : int { kQueryRawF32 = 0, kQueryElement = 1 };
@@ -138,7 +140,8 @@ __device__ __forceinline__ float finish_angular(float r, int* status) {
 struct WarpCtx {
     unsigned long long* list;  // L
     uint32_t* visited;
-    float* tile;       // 32 x 33 floats (always shared)
+    float* tile;       // 32 x kTileStride floats (always shared)
+    uint32_t* ids;     // 32 u32 scratch for compacting candidate ids (always shared)
     float* qs;         // query, natural layout: f32[dim] (or i8 words for ANGULAR_INT), shared
     float* xs;         // EMBEDDINGS scratch f32[dim], shared
     int lane;
@@ -161,12 +164,13 @@ __device__ __forceinline__ float ordered_lane_sum_bcast(float p) {
 // ------------------------------------------------------------------------------------------------------------------
 
 // ANGULAR f32, compile-time chunk count FULL (dim = 32*FULL + tail).  Query chunk values live in registers.
+// Rows are lane-permuted in HBM (see permute_rows_f32_kernel) so one LDG.128/64/32 per lane and group fetches a
+// lane's share of G*V chunks; all rows of a batch of 16 candidates are in flight before the first FMA.
 template <int FULL>
 struct DistF32 {
     static constexpr int V = (FULL % 4 == 0) ? 4 : ((FULL % 2 == 0) ? 2 : 1);
     static constexpr int G = FULL / V;
     static constexpr int NQ = FULL > 0 ? FULL : 1;
-    static constexpr int BATCH = FULL <= 4 ? 16 : 8;
     float q[NQ];
 
     __device__ __forceinline__ void load_query(const DeviceIndex& ix, const WarpCtx& c) {
@@ -174,42 +178,56 @@ struct DistF32 {
         for (int ch = 0; ch < FULL; ++ch) q[ch] = c.qs[ch * 32 + c.lane];
     }
 
+    static __device__ __forceinline__ void load_row(const char* lane_base, uint32_t id, uint32_t stride_bytes,
+                                                    float (&d)[NQ]) {
+        const float* row = reinterpret_cast<const float*>(lane_base + (size_t)id * stride_bytes);  // IMAD.WIDE.U32
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            if (V == 4) {
+                const float4 v = ldg_row_f4(row + g * 128);
+                d[g * 4 + 0] = v.x;
+                d[g * 4 + 1] = v.y;
+                d[g * 4 + 2] = v.z;
+                d[g * 4 + 3] = v.w;
+            } else if (V == 2) {
+                const float2 v = ldg_row_f2(row + g * 64);
+                d[g * 2 + 0] = v.x;
+                d[g * 2 + 1] = v.y;
+            } else {
+                d[g] = ldg_row_f1(row + g * 32);
+            }
+        }
+    }
+
     __device__ __forceinline__ float dists(const DeviceIndex& ix, WarpCtx& c, uint32_t my_id, int k) {
-        const float* base = static_cast<const float*>(ix.vectors);
-        const size_t stride = ix.row_stride;
+        const uint32_t stride_bytes = ix.row_stride * 4u;
         if (FULL > 0) {
-            for (int j0 = 0; j0 < k; j0 += BATCH) {
-                float data[BATCH][NQ];
+            const char* lane_base = static_cast<const char*>(ix.vectors) + c.lane * (V * 4);
+            for (int j0 = 0; j0 < k; j0 += 16) {
+                float data[16][NQ];
+                // 4 groups of 4 rows; a group is skipped as a whole (uniform branch), inside a group indices past
+                // the end re-load the last candidate (same sectors) instead of predicating every instruction off.
 #pragma unroll
-                for (int b = 0; b < BATCH; ++b) {
-                    const uint32_t id = __shfl_sync(kFullMask, my_id, (j0 + b) & 31);
-                    if (j0 + b < k) {
-                        const float* row = base + (size_t)id * stride + c.lane * V;
+                for (int g4 = 0; g4 < 4; ++g4) {
+                    if (j0 + g4 * 4 < k) {
 #pragma unroll
-                        for (int g = 0; g < G; ++g) {
-                            if (V == 4) {
-                                float4 v = ldg_row_f4(row + g * 128);
-                                data[b][g * 4 + 0] = v.x;
-                                data[b][g * 4 + 1] = v.y;
-                                data[b][g * 4 + 2] = v.z;
-                                data[b][g * 4 + 3] = v.w;
-                            } else if (V == 2) {
-                                float2 v = ldg_row_f2(row + g * 64);
-                                data[b][g * 2 + 0] = v.x;
-                                data[b][g * 2 + 1] = v.y;
-                            } else {
-                                data[b][g] = ldg_row_f1(row + g * 32);
-                            }
+                        for (int b = 0; b < 4; ++b) {
+                            const int idx = j0 + g4 * 4 + b;
+                            const uint32_t id = __shfl_sync(kFullMask, my_id, idx < k ? idx : k - 1);
+                            load_row(lane_base, id, stride_bytes, data[g4 * 4 + b]);
                         }
                     }
                 }
 #pragma unroll
-                for (int b = 0; b < BATCH; ++b) {
-                    if (j0 + b < k) {
-                        float p = 0.0f;
+                for (int g4 = 0; g4 < 4; ++g4) {
+                    if (j0 + g4 * 4 < k) {
 #pragma unroll
-                        for (int ch = 0; ch < FULL; ++ch) p = __fmaf_rn(data[b][ch], q[ch], p);
-                        c.tile[(j0 + b) * 33 + c.lane] = p;
+                        for (int b = 0; b < 4; ++b) {
+                            float p = 0.0f;
+#pragma unroll
+                            for (int ch = 0; ch < FULL; ++ch) p = __fmaf_rn(data[g4 * 4 + b][ch], q[ch], p);
+                            c.tile[(j0 + g4 * 4 + b) * kTileStride + c.lane] = p;
+                        }
                     }
                 }
             }
@@ -219,13 +237,20 @@ struct DistF32 {
         if (c.lane < k) {
             float r = 0.0f;
             if (FULL > 0) {
-                const float* t = c.tile + c.lane * 33;
+                const float4* t = reinterpret_cast<const float4*>(c.tile + c.lane * kTileStride);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) r = __fadd_rn(r, t[i]);
+                for (int i = 0; i < 8; ++i) {
+                    const float4 v = t[i];
+                    r = __fadd_rn(r, v.x);
+                    r = __fadd_rn(r, v.y);
+                    r = __fadd_rn(r, v.z);
+                    r = __fadd_rn(r, v.w);
+                }
             }
             const int tail = ix.tail;
             if (tail) {
-                const float* row = base + (size_t)my_id * stride + FULL * 32;
+                const float* row = reinterpret_cast<const float*>(static_cast<const char*>(ix.vectors) +
+                                                                   (size_t)my_id * stride_bytes) + FULL * 32;
                 const float* qt = c.qs + FULL * 32;
                 for (int t = 0; t < tail; ++t) r = __fmaf_rn(__ldg(row + t), qt[t], r);
             }
@@ -248,13 +273,13 @@ struct DistF32Generic {
             const float* row = base + (size_t)id * stride + c.lane;
             float p = 0.0f;
             for (int ch = 0; ch < full; ++ch) p = __fmaf_rn(ldg_row_f1(row + ch * 32), c.qs[ch * 32 + c.lane], p);
-            c.tile[j * 33 + c.lane] = p;
+            c.tile[j * kTileStride + c.lane] = p;
         }
         __syncwarp();
         float d = 0.0f;
         if (c.lane < k) {
             float r = 0.0f;
-            const float* t = c.tile + c.lane * 33;
+            const float* t = c.tile + c.lane * kTileStride;
 #pragma unroll
             for (int i = 0; i < 32; ++i) r = __fadd_rn(r, t[i]);
             const float* row = base + (size_t)my_id * stride + full * 32;
@@ -386,11 +411,18 @@ __device__ __forceinline__ bool vis_insert(uint32_t* tab, uint32_t slots, uint32
 // ------------------------------------------------------------------------------------------------------------------
 // search_for_neighbors (src/index/mod.rs:999-1037) on one layer.  On return the list holds the merged state;
 // *out_n is its length.  The result set (`res.into_sorted_vec()`) is the first min(|E|, ef) expanded entries.
+//
+// Bookkeeping (all warp-uniform): n = entries in L; cursor = every entry before it is expanded; while res is not
+// full n_exp counts the expanded entries of L; once res is full n_exp == ef and pos_thr is the position of res.peek()
+// (the ef-th expanded entry), thr_bits its distance.  Expanded entries behind pos_thr are dead weight.
+// The model of exactly this logic is tests/helpers/list_model.py::search_layer_model_v2 (validated on the CPU).
 // ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t warp_min_u32(unsigned mask, uint32_t v) { return __reduce_min_sync(mask, v); }
+
 template <class Dist>
 __device__ __forceinline__ void search_layer(const DeviceIndex& ix, WarpCtx& c, Dist& dist, const uint32_t* rows,
-                                          const uint32_t width, const uint32_t entrypoint, const uint32_t ef,
-                                          const uint32_t cap, const uint32_t vis_slots, uint32_t* out_n) {
+                                             const uint32_t width, const uint32_t entrypoint, const uint32_t ef,
+                                             const uint32_t cap, const uint32_t vis_slots, uint32_t* out_n) {
     unsigned long long* L = c.list;
     const int lane = c.lane;
     for (uint32_t i = lane; i < vis_slots; i += 32) c.visited[i] = kUnusedId;
@@ -413,13 +445,14 @@ __device__ __forceinline__ void search_layer(const DeviceIndex& ix, WarpCtx& c, 
         }
         __syncwarp();
     }
-    uint32_t n = 1;          // entries in L
-    uint32_t n_exp = 0;      // expanded entries in L
-    uint32_t cursor = 0;     // every entry before `cursor` is expanded
-    uint32_t thr_bits = 0;   // distance bits of the ef-th expanded entry (valid iff n_exp >= ef)
+    uint32_t n = 1;
+    uint32_t n_exp = 0;
+    uint32_t cursor = 0;
+    uint32_t pos_thr = 0;
+    uint32_t thr_bits = 0;
 
     while (true) {
-        // ---- pq.pop(): first unexpanded entry ----
+        // ---- pq.pop(): first unexpanded entry at or after the cursor ----
         int px = -1;
         for (uint32_t base = cursor & ~31u; base < n; base += 32) {
             const uint32_t j = base + lane;
@@ -432,31 +465,41 @@ __device__ __forceinline__ void search_layer(const DeviceIndex& ix, WarpCtx& c, 
         }
         if (px < 0) break;  // pq empty
         const unsigned long long x = L[px];
-        const uint32_t xd = key_dbits(x);
         const uint32_t xid = key_id(x);
-        if (n_exp >= ef && xd > thr_bits) break;  // res.is_full() && d > res.peek().0  (:1019-1021)
+        if (n_exp >= ef && key_dbits(x) > thr_bits) break;  // res.is_full() && d > res.peek().0  (:1019-1021)
 
         // ---- res.push((d, idx)) (:1023; max_size_heap.rs:18-32) ----
         __syncwarp();
         if (lane == 0) L[px] = x | kFlagExpanded;
         __syncwarp();
-        n_exp += 1;
         cursor = px + 1;
-        if (n_exp >= ef) {
-            // locate the ef-th expanded entry: res.peek()
-            uint32_t cnt = 0;
-            for (uint32_t base = 0; base < n; base += 32) {
+        n_exp += 1;
+        if (n_exp == ef) {
+            // res just became full: res.peek() is the last expanded entry of L
+            for (int base = (int)((n - 1) & ~31u); base >= 0; base -= 32) {
                 const uint32_t j = base + lane;
-                const bool fl = (j < n) && (L[j] >> 63);
-                const unsigned m = __ballot_sync(kFullMask, fl);
-                const uint32_t pc = __popc(m);
-                if (cnt + pc >= ef) {
-                    const uint32_t pos = base + __fns(m, 0, ef - cnt);
-                    thr_bits = key_dbits(L[pos]);
+                const unsigned m = __ballot_sync(kFullMask, (j < n) && (L[j] >> 63));
+                if (m) {
+                    pos_thr = base + 31 - __clz(m);
                     break;
                 }
-                cnt += pc;
             }
+            thr_bits = key_dbits(L[pos_thr]);
+        } else if (n_exp > ef) {
+            n_exp = ef;
+            if ((uint32_t)px < pos_thr) {
+                // the push evicted res.peek(): the new maximum is the previous expanded entry
+                for (int base = (int)((pos_thr - 1) & ~31u); base >= 0; base -= 32) {
+                    const uint32_t j = base + lane;
+                    const unsigned m = __ballot_sync(kFullMask, (j < pos_thr) && (L[j] >> 63));
+                    if (m) {
+                        pos_thr = base + 31 - __clz(m);
+                        break;
+                    }
+                }
+                thr_bits = key_dbits(L[pos_thr]);
+            }
+            // else: an equal-distance entry behind res.peek(): expanded but rejected by MaxSizeHeap::push
         }
         c.n_expand += 1;
 
@@ -479,8 +522,9 @@ __device__ __forceinline__ void search_layer(const DeviceIndex& ix, WarpCtx& c, 
                 return;
             }
             // compact the new ids to lanes 0..k-1 (any order: the push set is order independent)
-            const int src = __fns(nm, 0, lane + 1);
-            const uint32_t my_id = __shfl_sync(kFullMask, nb, src & 31);
+            if (is_new) c.ids[__popc(nm & lanemask_lt())] = nb;
+            __syncwarp();
+            const uint32_t my_id = c.ids[lane < k ? lane : 0];
             c.n_dist += k;
             const float d = dist.dists(ix, c, my_id, k);
             if (__any_sync(kFullMask, c.status & kStatusNotFinite)) {
@@ -491,52 +535,92 @@ __device__ __forceinline__ void search_layer(const DeviceIndex& ix, WarpCtx& c, 
             const unsigned long long my_key = make_key(d, my_id);
             // !res.is_full() || distance < res.peek().0   (:1029)
             const bool pass = (lane < k) && (n_exp < ef || key_dbits(my_key) < thr_bits);
-            unsigned pm = __ballot_sync(kFullMask, pass);
-            while (pm) {
-                const int j = __ffs(pm) - 1;
-                pm &= pm - 1;
-                const unsigned long long key = __shfl_sync(kFullMask, my_key, j);
-                // ---- pq.push(key): insert into the sorted list ----
-                int hi;  // highest index that moves up
-                if (n == cap) {
-                    const unsigned long long last = L[cap - 1];
-                    const uint32_t guard = key_dbits(L[ef - 1]);  // cap > ef
-                    if (key > (last & kKeyMask)) {
-                        // dropped without entering L: legal only if >= ef strictly closer entries exist
-                        if (!(guard < key_dbits(key))) c.status |= kStatusOverflow;
-                        continue;
+            const unsigned pm = __ballot_sync(kFullMask, pass);
+            if (pm == 0) continue;
+            const uint32_t m = __popc(pm);
+
+            // ---- pq.push for all passing keys at once: rank-based merge into the sorted list ----
+            // rank of my key among the current entries (binary search, all lanes in lock step)
+            uint32_t lo = 0, hi = n;
+            for (int it = 32 - __clz(n); it > 0; --it) {
+                const uint32_t mid = (lo + hi) >> 1;
+                const bool less = (lo < hi) && ((L[mid < n ? mid : n - 1] & kKeyMask) < my_key);
+                if (lo < hi) {
+                    if (less)
+                        lo = mid + 1;
+                    else
+                        hi = mid;
+                }
+            }
+            const uint32_t rank_l = lo;
+            uint32_t rank_n = 0;  // rank among the passing keys
+            for (unsigned t = pm; t; t &= t - 1) {
+                const unsigned long long kb = __shfl_sync(kFullMask, my_key, __ffs(t) - 1);
+                rank_n += (kb < my_key) ? 1u : 0u;
+            }
+            const uint32_t new_pos = rank_l + rank_n;
+            const uint32_t min_rank = warp_min_u32(kFullMask, pass ? rank_l : 0xFFFFFFFFu);
+            const uint32_t total = n + m;
+            uint32_t drop_min = 0xFFFFFFFFu;   // smallest distance among dropped entries
+            uint32_t drop_flagged = 0;
+            // existing entries at positions >= min_rank move up by the number of new keys ranked at or before them;
+            // rows are processed top-down so a write never lands on an entry that has not been read yet.
+            for (int base = (int)((n - 1) & ~31u); base >= (int)(min_rank & ~31u); base -= 32) {
+                const uint32_t j = base + lane;
+                const bool in = (j < n) && (j >= min_rank);
+                unsigned long long v = 0;
+                if (in) v = L[j];
+                uint32_t sh = 0;
+                for (unsigned t = pm; t; t &= t - 1) {
+                    const uint32_t r = __shfl_sync(kFullMask, rank_l, __ffs(t) - 1);
+                    sh += (r <= j) ? 1u : 0u;
+                }
+                const uint32_t np = j + sh;
+                __syncwarp();
+                if (in && np < cap) L[np] = v;
+                if (total > cap) {
+                    const bool dropped = in && np >= cap;
+                    const unsigned dm = __ballot_sync(kFullMask, dropped);
+                    if (dm) {
+                        drop_flagged += __popc(__ballot_sync(kFullMask, dropped && (v >> 63)));
+                        drop_min = min(drop_min, warp_min_u32(kFullMask, dropped ? key_dbits(v) : 0xFFFFFFFFu));
                     }
-                    if (!(guard < key_dbits(last))) c.status |= kStatusOverflow;
-                    if (last >> 63) n_exp -= 1;
-                    hi = (int)cap - 2;
+                }
+            }
+            __syncwarp();
+            if (pass && new_pos < cap) L[new_pos] = my_key;
+            __syncwarp();
+            if (total > cap) {
+                drop_min = min(drop_min, warp_min_u32(kFullMask, (pass && new_pos >= cap) ? key_dbits(my_key)
+                                                                                            : 0xFFFFFFFFu));
+                n = cap;
+                // an entry may leave L only if >= ef strictly closer entries remain (see "Exactness")
+                if (!(key_dbits(L[ef - 1]) < drop_min)) {
+                    c.status |= kStatusOverflow;
+                    *out_n = n;
+                    return;
+                }
+                if (n_exp >= ef) {
+                    if (pos_thr + m >= cap) {
+                        // res.peek() itself left L: res now spans evicted entries ("not full" regime); recount
+                        uint32_t cnt = 0;
+                        for (uint32_t base = 0; base < n; base += 32) {
+                            const uint32_t j = base + lane;
+                            cnt += __popc(__ballot_sync(kFullMask, (j < n) && (L[j] >> 63)));
+                        }
+                        n_exp = cnt < ef ? cnt : ef - 1;
+                    } else {
+                        pos_thr += m;  // every passing key is closer than res.peek()
+                    }
                 } else {
-                    hi = (int)n - 1;
-                    n += 1;
+                    n_exp -= drop_flagged;
                 }
-                int pos = 0;
-                for (int base = hi & ~31; base >= 0; base -= 32) {
-                    const int jj = base + lane;
-                    unsigned long long v = 0;
-                    bool in = jj <= hi;
-                    if (in) v = L[jj];
-                    const bool gt = in && ((v & kKeyMask) > key);
-                    __syncwarp();
-                    if (gt) L[jj + 1] = v;
-                    const unsigned stay = __ballot_sync(kFullMask, in && !gt);
-                    if (stay) {
-                        pos = base + __popc(stay);
-                        break;
-                    }
-                }
-                __syncwarp();
-                if (lane == 0) L[pos] = key;
-                __syncwarp();
-                if ((uint32_t)pos < cursor) cursor = pos;
+            } else {
+                n = total;
+                if (n_exp >= ef) pos_thr += m;
             }
-            if (c.status & kStatusOverflow) {
-                *out_n = n;
-                return;
-            }
+            const uint32_t min_pos = warp_min_u32(kFullMask, pass ? new_pos : 0xFFFFFFFFu);
+            if (min_pos < cursor) cursor = min_pos;
         }
     }
     *out_n = n;
@@ -624,10 +708,11 @@ __global__ void __launch_bounds__(32) search_kernel(const DeviceIndex ix, const 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WarpCtx c;
     c.lane = threadIdx.x;
-    // shared layout: tile | qs | xs | list | visited   (list/visited live in global memory on the slow path)
+    // shared layout: tile + id scratch | qs | xs | list | visited   (list/visited live in global memory on the slow path)
     unsigned char* sp = smem_raw;
     c.tile = reinterpret_cast<float*>(sp);
-    sp += 32 * 33 * sizeof(float);
+    c.ids = reinterpret_cast<uint32_t*>(sp + 32 * kTileStride * sizeof(float));
+    sp += kTileBytes;
     const uint32_t qbytes = (ix.kind == kAngularI8) ? ix.row_stride : ((ix.dim + 3u) & ~3u) * 4u;
     c.qs = reinterpret_cast<float*>(sp);
     sp += (qbytes + 15u) & ~15u;

@@ -181,9 +181,12 @@ class Elements:
         self._h = _handle if _handle is not None else lib().orc_elements_new(self.kind, dim)
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().orc_elements_free(self._h)
-            self._h = None
+        try:
+            if getattr(self, "_h", None):
+                lib().orc_elements_free(self._h)
+                self._h = None
+        except Exception:  # interpreter shutdown
+            pass
 
     @classmethod
     def angular(cls, raw, as_is=False):
@@ -269,9 +272,12 @@ class Granne:
         self.elements = elements
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().orc_index_free(self._h)
-            self._h = None
+        try:
+            if getattr(self, "_h", None):
+                lib().orc_index_free(self._h)
+                self._h = None
+        except Exception:  # interpreter shutdown
+            pass
 
     @classmethod
     def from_bytes(cls, index_bytes, elements):

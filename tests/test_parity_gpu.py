@@ -171,21 +171,25 @@ def test_duplicates_and_ties(oracle):
 
 
 def test_all_identical_vectors_take_the_exact_slow_path(oracle):
-    # every distance is equal: the reference expands the whole connected component (d > max is never true);
-    # the fast path's bounded list must detect the plateau and hand over to the slow path, which stays exact.
+    # every distance is equal and every node has ~30 neighbours (disjoint fan-outs): while res is not yet full the reference pushes every
+    # neighbour (src/index/mod.rs:1029), so the frontier holds a plateau of equal distances far wider than the fast
+    # path's bounded list.  The kernel must detect that it cannot drop entries exactly and hand the query to the slow
+    # path, which stays bit-exact.
     n, dim = 400, 8
     raw = np.tile(random_vectors(1, dim, seed=5), (n, 1))
     el = oracle.Elements.angular(raw)
-    # a ring graph written in granne's format through the oracle's writer
-    nb = [[(i + 1) % n, (i + 2) % n, (i - 1) % n] for i in range(n)]
-    ib = _index_from_lists(oracle, [nb])
+    nb = [sorted({(i * 30 + j) % n for j in range(1, 31)} - {i}) for i in range(n)]  # disjoint fan-outs
+    ib = _index_from_lists(oracle, [nb])  # written in granne's format through the oracle's list encoder
     g = oracle.Granne.from_bytes(ib, el)
     p = open_product(ib, "angular", el.to_bytes())
     q = random_vectors(8, dim, seed=6)
     ref, got = run_both(g, p, q, 20, 10)
     assert_parity(ref, got, "plateau")
     assert (got[3][:, 3] == 1).all()          # flagged: served by the slow path
-    assert (ref[3][:, 1] == n).all()           # the reference really expands every node
+    assert (ref[3][:, 1] > 20).all()           # equal-distance frontier entries are expanded beyond max_search
+    # the same index with a roomy max_search stays on the fast path
+    ref, got = run_both(g, p, q, 300, 10)
+    assert_parity(ref, got, "plateau ef=300")
     p.close()
 
 
