@@ -259,13 +259,21 @@ int read_file(const char* path, std::vector<uint8_t>* out) {
 // ---- launch configuration -----------------------------------------------------------------------------------------
 struct LaunchPlan {
     uint32_t list_cap, vis_slots, vis_upper;
+    int rows;  // fast list rows R (capacity 32*R), 0 = generic list
     size_t smem;
 };
 
 LaunchPlan make_plan(const Handle* h, uint32_t max_search) {
     const gb::DeviceIndex& d = h->dev;
     LaunchPlan p;
-    p.list_cap = std::max<uint32_t>(32, (max_search + 16 + 31) & ~31u);
+    // fast list: capacity 32*R with R odd (conflict-free lane-major access); slack >= 16 entries over max_search
+    p.rows = 0;
+    for (int r : {3, 7, 15, 31})
+        if (max_search + 16 <= 32u * r) {
+            p.rows = r;
+            break;
+        }
+    p.list_cap = p.rows ? 32u * p.rows : std::max<uint32_t>(32, (max_search + 16 + 31) & ~31u);
     const uint32_t deg = h->layer_max_degree.empty() ? 1 : std::max<uint32_t>(8, h->layer_max_degree.back());
     uint64_t want = std::max<uint64_t>(1024, (uint64_t)max_search * std::min<uint32_t>(deg, 64));
     want = (want + 31) & ~31ull;
@@ -285,12 +293,14 @@ LaunchPlan make_plan(const Handle* h, uint32_t max_search) {
     return p;
 }
 
-template <class Dist>
-int launch_search(Handle* h, const gb::SearchArgs& a, const LaunchPlan& plan, cudaStream_t stream) {
-    auto kern = gb::search_kernel<Dist>;
+template <class Dist, int R>
+int launch_kernels(Handle* h, const gb::SearchArgs& a, const LaunchPlan& plan, cudaStream_t stream) {
+    auto kern = gb::search_kernel<Dist, R>;
+    auto slow = gb::search_kernel<Dist, 0>;
     static std::atomic<bool> attr_set{false};
     if (!attr_set.load()) {
         GB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
+        GB_CUDA(cudaFuncSetAttribute(slow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
         attr_set.store(true);
     }
     // fast pass
@@ -318,10 +328,21 @@ int launch_search(Handle* h, const gb::SearchArgs& a, const LaunchPlan& plan, cu
     s.slow_pass = 1;
     s.work_counter = a.work_counter + 1;
     const size_t slow_smem = plan.smem - (size_t)plan.vis_slots * 4 - (size_t)plan.list_cap * 8;
-    kern<<<h->slow_ctas, 32, slow_smem, stream>>>(h->dev, s);
+    slow<<<h->slow_ctas, 32, slow_smem, stream>>>(h->dev, s);
     h->launches++;
     GB_CUDA(cudaGetLastError());
     return GRANNE_B200_OK;
+}
+
+template <class Dist>
+int launch_search(Handle* h, const gb::SearchArgs& a, const LaunchPlan& plan, cudaStream_t stream) {
+    switch (plan.rows) {
+        case 3: return launch_kernels<Dist, 3>(h, a, plan, stream);
+        case 7: return launch_kernels<Dist, 7>(h, a, plan, stream);
+        case 15: return launch_kernels<Dist, 15>(h, a, plan, stream);
+        case 31: return launch_kernels<Dist, 31>(h, a, plan, stream);
+        default: return launch_kernels<Dist, 0>(h, a, plan, stream);
+    }
 }
 
 int dispatch_search(Handle* h, const gb::SearchArgs& a, const LaunchPlan& plan, cudaStream_t stream) {

@@ -367,6 +367,7 @@ struct DistSum {
             r = __fmaf_rn(v, v, r);
         }
         const float norm = __fsqrt_rn(r);
+        __syncwarp();  // every lane has finished reading the un-normalised tail before anyone overwrites it
         if (norm > 0.0f)
             for (int i = c.lane; i < dim; i += 32) c.xs[i] = __fdiv_rn(c.xs[i], norm);
         __syncwarp();
@@ -627,6 +628,254 @@ __device__ __forceinline__ void search_layer(const DeviceIndex& ix, WarpCtx& c, 
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// search_for_neighbors, fast variant: same state machine as search_layer (above) with a cheaper list representation.
+//   * keys are split into two u32 arrays in shared memory: Ld[j] = distance bits | expanded flag (bit 31) and
+//     Li[j] = id, sorted by (distance, id); capacity is 32*R (R compile time, odd -> conflict-free lane-major access);
+//   * all passing keys of one expansion are merged in one pass: every lane binary-searches the rank of its key, a
+//     shared-memory histogram of the ranks is prefix-summed with lane-major ownership (lane l owns positions
+//     [R*l, R*l+R)), which yields for every existing entry how far it moves and for every new key where it lands;
+//     the move itself goes through registers (read everything, sync, write), so it is race free in place.
+// The cost of an expansion no longer depends on how many keys pass.  `hist` aliases the distance tile (free here).
+// ------------------------------------------------------------------------------------------------------------------
+template <class Dist, int R>
+__device__ __forceinline__ void search_layer_fast(const DeviceIndex& ix, WarpCtx& c, Dist& dist, const uint32_t* rows,
+                                                  const uint32_t width, const uint32_t entrypoint, const uint32_t ef,
+                                                  const uint32_t vis_slots, uint32_t* out_n) {
+    constexpr uint32_t cap = 32u * R;
+    constexpr uint32_t kFlag = 0x80000000u, kDMask = 0x7FFFFFFFu;
+    uint32_t* Ld = reinterpret_cast<uint32_t*>(c.list);
+    uint32_t* Li = Ld + cap;
+    uint32_t* hist = reinterpret_cast<uint32_t*>(c.tile);  // cap + 1 counters
+    const int lane = c.lane;
+    for (uint32_t i = lane; i < vis_slots; i += 32) c.visited[i] = kUnusedId;
+    __syncwarp();
+    const uint32_t vis_limit = vis_slots - (vis_slots >> 3);
+    uint32_t vis_count = 1;
+
+    {
+        const float d0 = dist.dists(ix, c, entrypoint, 1);
+        c.n_dist += 1;
+        if (__any_sync(kFullMask, c.status & kStatusNotFinite)) {
+            c.status |= kStatusNotFinite;
+            *out_n = 0;
+            return;
+        }
+        if (lane == 0) {
+            Ld[0] = __float_as_uint(d0);
+            Li[0] = entrypoint;
+            vis_insert(c.visited, vis_slots, entrypoint);
+        }
+        __syncwarp();
+    }
+    uint32_t n = 1, n_exp = 0, cursor = 0, pos_thr = 0, thr_bits = 0;
+
+    while (true) {
+        // ---- pq.pop() ----
+        int px = -1;
+        for (uint32_t base = cursor & ~31u; base < n; base += 32) {
+            const uint32_t j = base + lane;
+            const bool un = (j < n) && (j >= cursor) && !(Ld[j] & kFlag);
+            const unsigned m = __ballot_sync(kFullMask, un);
+            if (m) {
+                px = base + __ffs(m) - 1;
+                break;
+            }
+        }
+        if (px < 0) break;
+        const uint32_t xd = Ld[px];  // unflagged
+        const uint32_t xid = Li[px];
+        if (n_exp >= ef && xd > thr_bits) break;
+
+        // ---- res.push ----
+        __syncwarp();
+        if (lane == 0) Ld[px] = xd | kFlag;
+        __syncwarp();
+        cursor = px + 1;
+        n_exp += 1;
+        if (n_exp == ef) {
+            for (int base = (int)((n - 1) & ~31u); base >= 0; base -= 32) {
+                const uint32_t j = base + lane;
+                const unsigned m = __ballot_sync(kFullMask, (j < n) && (Ld[j] & kFlag));
+                if (m) {
+                    pos_thr = base + 31 - __clz(m);
+                    break;
+                }
+            }
+            thr_bits = Ld[pos_thr] & kDMask;
+        } else if (n_exp > ef) {
+            n_exp = ef;
+            if ((uint32_t)px < pos_thr) {
+                for (int base = (int)((pos_thr - 1) & ~31u); base >= 0; base -= 32) {
+                    const uint32_t j = base + lane;
+                    const unsigned m = __ballot_sync(kFullMask, (j < pos_thr) && (Ld[j] & kFlag));
+                    if (m) {
+                        pos_thr = base + 31 - __clz(m);
+                        break;
+                    }
+                }
+                thr_bits = Ld[pos_thr] & kDMask;
+            }
+        }
+        c.n_expand += 1;
+
+        // ---- neighbours ----
+        const uint32_t* row = rows + (size_t)xid * width;
+        for (uint32_t w0 = 0; w0 < width; w0 += 32) {
+            const uint32_t nb = (w0 + lane < width) ? __ldg(row + w0 + lane) : kUnusedId;
+            const bool valid = nb != kUnusedId;
+            const unsigned vm = __ballot_sync(kFullMask, valid);
+            if (vm == 0) break;
+            c.n_nbr += __popc(vm);
+            const bool is_new = valid && vis_insert(c.visited, vis_slots, nb);
+            const unsigned nm = __ballot_sync(kFullMask, is_new);
+            const int k = __popc(nm);
+            if (k == 0) continue;
+            vis_count += k;
+            if (vis_count > vis_limit) {
+                c.status |= kStatusOverflow;
+                *out_n = n;
+                return;
+            }
+            if (is_new) c.ids[__popc(nm & lanemask_lt())] = nb;
+            __syncwarp();
+            const uint32_t my_id = c.ids[lane < k ? lane : 0];
+            c.n_dist += k;
+            const float d = dist.dists(ix, c, my_id, k);
+            if (__any_sync(kFullMask, c.status & kStatusNotFinite)) {
+                c.status |= kStatusNotFinite;
+                *out_n = n;
+                return;
+            }
+            const uint32_t my_d = __float_as_uint(d);
+            const bool pass = (lane < k) && (n_exp < ef || my_d < thr_bits);
+            const unsigned pm = __ballot_sync(kFullMask, pass);
+            if (pm == 0) continue;
+            const uint32_t m = __popc(pm);
+
+            // zero the histogram (lane-major) while the binary search runs
+#pragma unroll
+            for (int t = 0; t < R; ++t) hist[R * lane + t] = 0;
+            if (lane == 0) hist[cap] = 0;
+            // rank of my key among the entries: lower bound on the distance, refined by id on exact ties
+            uint32_t lo = 0, hi = n;
+            for (int it = 32 - __clz(n); it > 0; --it) {
+                const uint32_t mid = (lo + hi) >> 1;
+                const uint32_t v = Ld[mid < n ? mid : n - 1] & kDMask;
+                if (lo < hi) {
+                    if (v < my_d)
+                        lo = mid + 1;
+                    else
+                        hi = mid;
+                }
+            }
+            while (lo < n && (Ld[lo] & kDMask) == my_d && Li[lo] < my_id) ++lo;  // (d, id) tuple order
+            const uint32_t rank_l = lo;
+            __syncwarp();
+            if (pass) atomicAdd(hist + rank_l, 1u);
+            __syncwarp();
+            // inclusive prefix over the histogram, lane-major: sh(j) = number of new keys ranked at or before entry j
+            uint32_t pre[R];
+            uint32_t run = 0;
+#pragma unroll
+            for (int t = 0; t < R; ++t) {
+                run += hist[R * lane + t];
+                pre[t] = run;
+            }
+            uint32_t incl = run;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(kFullMask, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const uint32_t offset = incl - run;
+            // read my entries into registers, publish the prefix sums (for the new keys' positions)
+            uint32_t dv[R], iv[R];
+#pragma unroll
+            for (int t = 0; t < R; ++t) {
+                const uint32_t j = R * lane + t;
+                dv[t] = 0;
+                iv[t] = 0;
+                if (j < n) {
+                    dv[t] = Ld[j];
+                    iv[t] = Li[j];
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int t = 0; t < R; ++t) hist[R * lane + t] = offset + pre[t];
+            __syncwarp();
+            // position of my key: its rank + the new keys ranked before it (+ order among keys of the same gap)
+            uint32_t before = (pass && rank_l > 0) ? hist[rank_l - 1] : 0;
+            const unsigned peers = __match_any_sync(kFullMask, pass ? rank_l : (0x80000000u | lane));
+            const unsigned multi = __ballot_sync(kFullMask, pass && (peers & (peers - 1)));
+            for (unsigned t = multi; t; t &= t - 1) {
+                const int j = __ffs(t) - 1;
+                const uint32_t rj = __shfl_sync(kFullMask, rank_l, j);
+                const uint32_t dj = __shfl_sync(kFullMask, my_d, j);
+                const uint32_t ij = __shfl_sync(kFullMask, my_id, j);
+                if (pass && j != lane && rj == rank_l && (dj < my_d || (dj == my_d && ij < my_id))) before += 1;
+            }
+            const uint32_t new_pos = rank_l + before;
+            const uint32_t total = n + m;
+            uint32_t drop_min = 0xFFFFFFFFu, drop_flagged = 0;
+#pragma unroll
+            for (int t = 0; t < R; ++t) {
+                const uint32_t j = R * lane + t;
+                const uint32_t sh = offset + pre[t];
+                if (j < n && sh > 0) {
+                    const uint32_t np = j + sh;
+                    if (np < cap) {
+                        Ld[np] = dv[t];
+                        Li[np] = iv[t];
+                    } else {
+                        drop_min = min(drop_min, dv[t] & kDMask);
+                        drop_flagged += dv[t] >> 31;
+                    }
+                }
+            }
+            if (pass) {
+                if (new_pos < cap) {
+                    Ld[new_pos] = my_d;
+                    Li[new_pos] = my_id;
+                } else {
+                    drop_min = min(drop_min, my_d);
+                }
+            }
+            __syncwarp();
+            if (total > cap) {
+                drop_min = warp_min_u32(kFullMask, drop_min);
+                n = cap;
+                if (!((Ld[ef - 1] & kDMask) < drop_min)) {
+                    c.status |= kStatusOverflow;
+                    *out_n = n;
+                    return;
+                }
+                if (n_exp >= ef) {
+                    if (pos_thr + m >= cap) {
+                        uint32_t cnt = 0;
+                        for (uint32_t base = 0; base < n; base += 32) {
+                            const uint32_t j = base + lane;
+                            cnt += __popc(__ballot_sync(kFullMask, (j < n) && (Ld[j] & kFlag)));
+                        }
+                        n_exp = cnt < ef ? cnt : ef - 1;
+                    } else {
+                        pos_thr += m;
+                    }
+                } else {
+                    n_exp -= __reduce_add_sync(kFullMask, drop_flagged);
+                }
+            } else {
+                n = total;
+                if (n_exp >= ef) pos_thr += m;
+            }
+            const uint32_t min_pos = warp_min_u32(kFullMask, pass ? new_pos : 0xFFFFFFFFu);
+            if (min_pos < cursor) cursor = min_pos;
+        }
+    }
+    *out_n = n;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // query construction (the `Elements::Element` the reference's callers build)
 // ------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void prepare_query(const DeviceIndex& ix, const SearchArgs& a, WarpCtx& c,
@@ -703,7 +952,9 @@ __device__ __forceinline__ void prepare_query(const DeviceIndex& ix, const Searc
 // ------------------------------------------------------------------------------------------------------------------
 // Granne::search for a batch (src/index/mod.rs:140-150, 962-997): persistent warps over a work counter.
 // ------------------------------------------------------------------------------------------------------------------
-template <class Dist>
+// R == 0: generic list (64-bit keys, any capacity, shared or global memory) — the slow pass and very large max_search.
+// R  > 0: fast list with capacity 32*R for the bottom layer (upper layers always use R = 1).
+template <class Dist, int R>
 __global__ void __launch_bounds__(32) search_kernel(const DeviceIndex ix, const SearchArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WarpCtx c;
@@ -753,45 +1004,81 @@ __global__ void __launch_bounds__(32) search_kernel(const DeviceIndex ix, const 
         uint32_t found = 0;
         if (ix.num_layers > 0 && !(c.status & kStatusNotFinite)) {
             // find_entrypoint (:984-997): max_search = 1 descent through the upper layers, then the bottom layer
-            // with the caller's max_search (:970-973).  One call site so the distance engine stays in registers.
+            // with the caller's max_search (:970-973).
             uint32_t entrypoint = 0;
-            const uint32_t cap1 = list_cap < 32 ? list_cap : 32;
-            for (int l = 0; l < ix.num_layers && c.status == 0; ++l) {
-                const bool bottom = (l + 1 == ix.num_layers);
-                search_layer(ix, c, dist, ix.layer_rows[l], ix.layer_width[l], entrypoint, bottom ? a.max_search : 1u,
-                             bottom ? list_cap : cap1, bottom ? vis_slots : vis_upper, &n);
-                if (bottom || c.status) break;
-                // res[0]: first expanded entry
-                uint32_t ep = 0;
-                for (uint32_t base = 0; base < n; base += 32) {
-                    const uint32_t j = base + c.lane;
-                    const bool fl = (j < n) && (c.list[j] >> 63);
-                    const unsigned m = __ballot_sync(kFullMask, fl);
-                    if (m) {
-                        ep = key_id(c.list[base + __ffs(m) - 1]);
-                        break;
+            const int bl = ix.num_layers - 1;
+            if (R == 0) {
+                const uint32_t cap1 = list_cap < 32 ? list_cap : 32;
+                for (int l = 0; l <= bl && c.status == 0; ++l) {
+                    const bool bottom = (l == bl);
+                    search_layer(ix, c, dist, ix.layer_rows[l], ix.layer_width[l], entrypoint,
+                                 bottom ? a.max_search : 1u, bottom ? list_cap : cap1,
+                                 bottom ? vis_slots : vis_upper, &n);
+                    if (bottom || c.status) break;
+                    uint32_t ep = 0;  // res[0]: first expanded entry
+                    for (uint32_t base = 0; base < n; base += 32) {
+                        const uint32_t j = base + c.lane;
+                        const unsigned m = __ballot_sync(kFullMask, (j < n) && (c.list[j] >> 63));
+                        if (m) {
+                            ep = key_id(c.list[base + __ffs(m) - 1]);
+                            break;
+                        }
                     }
+                    entrypoint = ep;
                 }
-                entrypoint = ep;
-            }
-            if (c.status == 0) {
-                // res.into_sorted_vec().take(num_neighbors) (:974-977, :1036)
-                const uint32_t limit = a.max_search < k ? a.max_search : k;
-                uint32_t cnt = 0;
-                for (uint32_t base = 0; base < n && cnt < limit; base += 32) {
-                    const uint32_t j = base + c.lane;
-                    unsigned long long v = 0;
-                    if (j < n) v = c.list[j];
-                    const bool fl = (j < n) && (v >> 63);
-                    const unsigned m = __ballot_sync(kFullMask, fl);
-                    const uint32_t rank = cnt + __popc(m & lanemask_lt());
-                    if (fl && rank < limit) {
-                        a.out_ids[qi * k + rank] = key_id(v);
-                        a.out_dists[qi * k + rank] = __uint_as_float(key_dbits(v));
+                if (c.status == 0) {
+                    // res.into_sorted_vec().take(num_neighbors) (:974-977, :1036)
+                    const uint32_t limit = a.max_search < k ? a.max_search : k;
+                    uint32_t cnt = 0;
+                    for (uint32_t base = 0; base < n && cnt < limit; base += 32) {
+                        const uint32_t j = base + c.lane;
+                        unsigned long long v = 0;
+                        if (j < n) v = c.list[j];
+                        const bool fl = (j < n) && (v >> 63);
+                        const unsigned m = __ballot_sync(kFullMask, fl);
+                        const uint32_t rank = cnt + __popc(m & lanemask_lt());
+                        if (fl && rank < limit) {
+                            a.out_ids[qi * k + rank] = key_id(v);
+                            a.out_dists[qi * k + rank] = __uint_as_float(key_dbits(v));
+                        }
+                        cnt += __popc(m);
                     }
-                    cnt += __popc(m);
+                    found = cnt < limit ? cnt : limit;
                 }
-                found = cnt < limit ? cnt : limit;
+            } else {
+                constexpr int RB = R > 0 ? R : 1;
+                const uint32_t* Ld = reinterpret_cast<const uint32_t*>(c.list);
+                for (int l = 0; l < bl && c.status == 0; ++l) {
+                    search_layer_fast<Dist, 1>(ix, c, dist, ix.layer_rows[l], ix.layer_width[l], entrypoint, 1u,
+                                               vis_upper, &n);
+                    if (c.status) break;
+                    uint32_t ep = 0;  // res[0] (capacity 32: a single row)
+                    const unsigned m = __ballot_sync(kFullMask, ((uint32_t)c.lane < n) && (Ld[c.lane] >> 31));
+                    if (m) ep = Ld[32 + __ffs(m) - 1];  // Li = Ld + 32 for R = 1
+                    entrypoint = ep;
+                }
+                if (c.status == 0)
+                    search_layer_fast<Dist, RB>(ix, c, dist, ix.layer_rows[bl], ix.layer_width[bl], entrypoint,
+                                                a.max_search, vis_slots, &n);
+                if (c.status == 0) {
+                    const uint32_t* Li = Ld + 32u * RB;
+                    const uint32_t limit = a.max_search < k ? a.max_search : k;
+                    uint32_t cnt = 0;
+                    for (uint32_t base = 0; base < n && cnt < limit; base += 32) {
+                        const uint32_t j = base + c.lane;
+                        uint32_t v = 0;
+                        if (j < n) v = Ld[j];
+                        const bool fl = (j < n) && (v >> 31);
+                        const unsigned m = __ballot_sync(kFullMask, fl);
+                        const uint32_t rank = cnt + __popc(m & lanemask_lt());
+                        if (fl && rank < limit) {
+                            a.out_ids[qi * k + rank] = Li[j];
+                            a.out_dists[qi * k + rank] = __uint_as_float(v & 0x7FFFFFFFu);
+                        }
+                        cnt += __popc(m);
+                    }
+                    found = cnt < limit ? cnt : limit;
+                }
             }
         }
         if (c.status & kStatusOverflow) {

@@ -76,7 +76,7 @@ def _key(dbits, idx):
     return (int(dbits) << 32) | int(idx)
 
 
-def search_layer_model_v2(get_neighbors, dist_bits, entrypoint, ef, cap, batch=32):
+def search_layer_model_v2(get_neighbors, dist_bits, entrypoint, ef, cap, batch=32, trace=None):
     """dist_bits(id) -> u32 bit pattern of the (non-negative) f32 distance.  Returns (res, n_dist, n_expand)."""
     assert cap > ef
     L = [0] * cap
@@ -85,6 +85,10 @@ def search_layer_model_v2(get_neighbors, dist_bits, entrypoint, ef, cap, batch=3
     L[0] = _key(dist_bits(entrypoint), entrypoint)
     n, n_exp, cursor = 1, 0, 0
     pos_thr, thr = -1, 0  # valid iff n_exp >= ef
+
+    def ev(name):
+        if trace is not None:
+            trace[name] = trace.get(name, 0) + 1
 
     def first_unexpanded(start):
         for j in range(start, n):
@@ -104,10 +108,12 @@ def search_layer_model_v2(get_neighbors, dist_bits, entrypoint, ef, cap, batch=3
         cursor = px + 1
         n_exp += 1
         if n_exp == ef:
+            ev("became_full")
             # res just became full: its max is the last expanded entry of L
             pos_thr = max(j for j in range(n) if L[j] & FLAG)
             thr = (L[pos_thr] >> 32) & 0x7FFFFFFF
         elif n_exp > ef:
+            ev("expand_before_thr" if px < pos_thr else "expand_tie_behind_thr")
             if px < pos_thr:
                 # MaxSizeHeap::push replaced the max: new max = previous expanded entry before the old one
                 j = pos_thr - 1
@@ -160,6 +166,7 @@ def search_layer_model_v2(get_neighbors, dist_bits, entrypoint, ef, cap, batch=3
             for p, v in merged.items():
                 L[p] = v
             if dropped:
+                ev("drop_batch")
                 guard = (L[ef - 1] >> 32) & 0x7FFFFFFF
                 dmin = min((v >> 32) & 0x7FFFFFFF for v in dropped)
                 if not guard < dmin:
@@ -168,6 +175,7 @@ def search_layer_model_v2(get_neighbors, dist_bits, entrypoint, ef, cap, batch=3
                 if n_exp >= ef:
                     # every inserted key is < thr entry: it moves up by m
                     if pos_thr + m >= cap:
+                        ev("thr_fell_off")
                         # the res max itself fell off: res now spans evicted entries -> "not full" regime
                         n_exp = sum(1 for j in range(nn) if L[j] & FLAG)
                         assert n_exp < ef
