@@ -60,6 +60,9 @@ struct Workspace {
     // slow path
     unsigned long long* d_slow_list = nullptr;
     uint32_t* d_slow_vis = nullptr;
+    // fast pass: per-CTA visited tables in global memory
+    uint32_t* d_vis = nullptr;
+    size_t vis_cap = 0;  // u32 entries
 };
 
 }  // namespace
@@ -259,13 +262,22 @@ int read_file(const char* path, std::vector<uint8_t>* out) {
 // ---- launch configuration -----------------------------------------------------------------------------------------
 struct LaunchPlan {
     uint32_t list_cap, vis_slots, vis_upper;
-    int rows;  // fast list rows R (capacity 32*R), 0 = generic list
-    size_t smem;
+    int rows;           // fast list rows R (capacity 32*R), 0 = generic list
+    uint32_t stg_rows;  // candidate rows per bulk-copy batch (staged distance engines only)
+    size_t base_smem;   // tile + mbarrier + query (+ embeddings scratch) + staging
+    size_t smem;        // fast pass total
+    bool staged;
 };
+
+bool is_staged_kind(const gb::DeviceIndex& d) {
+    // DistF32<FULL> with FULL > 0 (see dispatch_search)
+    return d.kind == gb::kAngularF32 && d.full > 0 && !(d.vec_group == 1 && d.full > 4) &&
+           (d.full <= 4 || d.full == 6 || d.full == 8);
+}
 
 LaunchPlan make_plan(const Handle* h, uint32_t max_search) {
     const gb::DeviceIndex& d = h->dev;
-    LaunchPlan p;
+    LaunchPlan p{};
     // fast list: capacity 32*R with R odd (conflict-free lane-major access); slack >= 16 entries over max_search
     p.rows = 0;
     for (int r : {3, 7, 15, 31})
@@ -278,9 +290,24 @@ LaunchPlan make_plan(const Handle* h, uint32_t max_search) {
     uint64_t want = std::max<uint64_t>(1024, (uint64_t)max_search * std::min<uint32_t>(deg, 64));
     want = (want + 31) & ~31ull;
     const uint32_t qbytes = (d.kind == gb::kAngularI8) ? d.row_stride : ((d.dim + 3u) & ~3u) * 4u;
-    const size_t fixed = gb::kTileBytes + ((qbytes + 15u) & ~15u) * (d.kind == gb::kSumEmbeddings ? 2 : 1) +
-                         (size_t)p.list_cap * 8;
+    size_t base = gb::kTileBytes + 16 + ((qbytes + 15u) & ~15u) * (d.kind == gb::kSumEmbeddings ? 2 : 1);
+    p.staged = is_staged_kind(d);
+    p.stg_rows = 0;
+    if (p.staged) {
+        const uint32_t row_bytes = d.full * 128u;
+        p.stg_rows = std::min<uint32_t>(16, std::max<uint32_t>(4, (8192u / row_bytes) & ~3u));
+        base = ((base + 127) & ~size_t(127)) + (size_t)p.stg_rows * row_bytes;
+    }
+    p.base_smem = base;
     const size_t budget = h->smem_optin;
+    if (p.rows) {
+        // fast pass: list in shared memory, visited set in global memory
+        p.vis_slots = (uint32_t)want;
+        p.vis_upper = std::min<uint32_t>(1024, p.vis_slots);
+        p.smem = base + gb::fast_list_bytes(p.rows);
+        return p;
+    }
+    const size_t fixed = base + (size_t)p.list_cap * 8;
     if (fixed + 4096 > budget) {  // caller rejects: the candidate list alone does not fit
         p.vis_slots = p.vis_upper = 0;
         p.smem = 0;
@@ -294,7 +321,7 @@ LaunchPlan make_plan(const Handle* h, uint32_t max_search) {
 }
 
 template <class Dist, int R>
-int launch_kernels(Handle* h, const gb::SearchArgs& a, const LaunchPlan& plan, cudaStream_t stream) {
+int launch_kernels(Handle* h, Workspace* w, gb::SearchArgs a, const LaunchPlan& plan, cudaStream_t stream) {
     auto kern = gb::search_kernel<Dist, R>;
     auto slow = gb::search_kernel<Dist, 0>;
     static std::atomic<bool> attr_set{false};
@@ -320,6 +347,19 @@ int launch_kernels(Handle* h, const gb::SearchArgs& a, const LaunchPlan& plan, c
     if (occ < 1) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "max_search too large for the shared-memory workspace");
     const unsigned long long slots = (unsigned long long)occ * h->num_sms;
     const unsigned grid = (unsigned)std::min<unsigned long long>(a.nq, slots);
+    if (R > 0) {
+        // per-CTA visited tables (global memory, L2 resident); sized for a full wave so later calls reuse it
+        const size_t need = (size_t)slots * plan.vis_slots;
+        if (need > w->vis_cap) {
+            GB_CUDA(cudaStreamSynchronize(stream));
+            cudaFree(w->d_vis);
+            w->d_vis = nullptr;
+            w->vis_cap = 0;
+            GB_CUDA(cudaMalloc(&w->d_vis, need * sizeof(uint32_t)));
+            w->vis_cap = need;
+        }
+        a.vis_global = w->d_vis;
+    }
     kern<<<grid, 32, plan.smem, stream>>>(h->dev, a);
     h->launches++;
     GB_CUDA(cudaGetLastError());
@@ -327,44 +367,43 @@ int launch_kernels(Handle* h, const gb::SearchArgs& a, const LaunchPlan& plan, c
     gb::SearchArgs s = a;
     s.slow_pass = 1;
     s.work_counter = a.work_counter + 1;
-    const size_t slow_smem = plan.smem - (size_t)plan.vis_slots * 4 - (size_t)plan.list_cap * 8;
-    slow<<<h->slow_ctas, 32, slow_smem, stream>>>(h->dev, s);
+    slow<<<h->slow_ctas, 32, plan.base_smem, stream>>>(h->dev, s);
     h->launches++;
     GB_CUDA(cudaGetLastError());
     return GRANNE_B200_OK;
 }
 
 template <class Dist>
-int launch_search(Handle* h, const gb::SearchArgs& a, const LaunchPlan& plan, cudaStream_t stream) {
+int launch_search(Handle* h, Workspace* w, const gb::SearchArgs& a, const LaunchPlan& plan, cudaStream_t stream) {
     switch (plan.rows) {
-        case 3: return launch_kernels<Dist, 3>(h, a, plan, stream);
-        case 7: return launch_kernels<Dist, 7>(h, a, plan, stream);
-        case 15: return launch_kernels<Dist, 15>(h, a, plan, stream);
-        case 31: return launch_kernels<Dist, 31>(h, a, plan, stream);
-        default: return launch_kernels<Dist, 0>(h, a, plan, stream);
+        case 3: return launch_kernels<Dist, 3>(h, w, a, plan, stream);
+        case 7: return launch_kernels<Dist, 7>(h, w, a, plan, stream);
+        case 15: return launch_kernels<Dist, 15>(h, w, a, plan, stream);
+        case 31: return launch_kernels<Dist, 31>(h, w, a, plan, stream);
+        default: return launch_kernels<Dist, 0>(h, w, a, plan, stream);
     }
 }
 
-int dispatch_search(Handle* h, const gb::SearchArgs& a, const LaunchPlan& plan, cudaStream_t stream) {
+int dispatch_search(Handle* h, Workspace* w, const gb::SearchArgs& a, const LaunchPlan& plan, cudaStream_t stream) {
     const gb::DeviceIndex& d = h->dev;
     switch (d.kind) {
         case gb::kAngularI8:
-            return launch_search<gb::DistI8>(h, a, plan, stream);
+            return launch_search<gb::DistI8>(h, w, a, plan, stream);
         case gb::kSumEmbeddings:
-            return launch_search<gb::DistSum>(h, a, plan, stream);
+            return launch_search<gb::DistSum>(h, w, a, plan, stream);
         default:
             break;
     }
-    if (d.vec_group == 1 && d.full > 4) return launch_search<gb::DistF32Generic>(h, a, plan, stream);
+    if (d.vec_group == 1 && d.full > 4) return launch_search<gb::DistF32Generic>(h, w, a, plan, stream);
     switch (d.full) {
-        case 0: return launch_search<gb::DistF32<0>>(h, a, plan, stream);
-        case 1: return launch_search<gb::DistF32<1>>(h, a, plan, stream);
-        case 2: return launch_search<gb::DistF32<2>>(h, a, plan, stream);
-        case 3: return launch_search<gb::DistF32<3>>(h, a, plan, stream);
-        case 4: return launch_search<gb::DistF32<4>>(h, a, plan, stream);
-        case 6: return launch_search<gb::DistF32<6>>(h, a, plan, stream);
-        case 8: return launch_search<gb::DistF32<8>>(h, a, plan, stream);
-        default: return launch_search<gb::DistF32Generic>(h, a, plan, stream);
+        case 0: return launch_search<gb::DistF32<0>>(h, w, a, plan, stream);
+        case 1: return launch_search<gb::DistF32<1>>(h, w, a, plan, stream);
+        case 2: return launch_search<gb::DistF32<2>>(h, w, a, plan, stream);
+        case 3: return launch_search<gb::DistF32<3>>(h, w, a, plan, stream);
+        case 4: return launch_search<gb::DistF32<4>>(h, w, a, plan, stream);
+        case 6: return launch_search<gb::DistF32<6>>(h, w, a, plan, stream);
+        case 8: return launch_search<gb::DistF32<8>>(h, w, a, plan, stream);
+        default: return launch_search<gb::DistF32Generic>(h, w, a, plan, stream);
     }
 }
 
@@ -403,6 +442,7 @@ void ws_destroy(Workspace* w) {
     cudaFree(w->d_error);
     cudaFree(w->d_slow_list);
     cudaFree(w->d_slow_vis);
+    cudaFree(w->d_vis);
     if (w->h_pinned) cudaFreeHost(w->h_pinned);
     if (w->stream) cudaStreamDestroy(w->stream);
 }
@@ -497,7 +537,9 @@ int enqueue_search(Handle* h, Workspace* w, const void* d_queries, size_t nq, in
     a.slow_list_cap = h->slow_list_cap;
     a.slow_vis_slots = h->slow_vis_slots;
     a.slow_pass = 0;
-    return dispatch_search(h, a, plan, stream);
+    a.stg_rows = plan.stg_rows;
+    a.vis_global = nullptr;
+    return dispatch_search(h, w, a, plan, stream);
 }
 
 int error_from_bits(int bits) {

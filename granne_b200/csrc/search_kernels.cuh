@@ -73,6 +73,8 @@ struct SearchArgs {
     uint32_t list_cap;        // C for the bottom layer
     uint32_t vis_slots;       // visited slots for the bottom layer
     uint32_t vis_slots_upper; // visited slots for the max_search = 1 descents
+    uint32_t* vis_global;     // fast pass: one table of vis_slots u32 per CTA in global memory (L2 resident)
+    uint32_t stg_rows;        // fast pass: candidate rows per bulk-copy batch (0 = this element kind loads directly)
     uint32_t* out_ids;
     float* out_dists;
     uint32_t* out_counts;
@@ -144,11 +146,44 @@ struct WarpCtx {
     uint32_t* ids;     // 32 u32 scratch for compacting candidate ids (always shared)
     float* qs;         // query, natural layout: f32[dim] (or i8 words for ANGULAR_INT), shared
     float* xs;         // EMBEDDINGS scratch f32[dim], shared
+    unsigned char* stg;  // staging tile for bulk-copied candidate rows (shared, 128-byte aligned)
+    uint32_t stg_rows;   // rows that fit in the staging tile (<= 16)
+    uint32_t bar;        // shared-space address of the mbarrier the bulk copies signal
+    uint32_t phase;      // its current phase parity
     int lane;
     int status;
     int q_norm_i8;     // ANGULAR_INT: dy = sum q^2
-    unsigned long long n_dist, n_expand, n_nbr;
+    uint32_t n_dist, n_expand, n_nbr;
 };
+
+// ---- mbarrier + 1-D bulk copy (TMA, UBLKCP) helpers ----------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+// global -> shared, `bytes` multiple of 16, both addresses 16-byte aligned; completion is counted on `bar`.
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
 
 // Strictly ordered sum of the 32 lane partials of ONE value (used where only a single candidate is live):
 // r = 0; for i in 0..32 { r += chunk[i] }   (src/math.rs:27-30).  All lanes return the same r.
@@ -164,13 +199,16 @@ __device__ __forceinline__ float ordered_lane_sum_bcast(float p) {
 // ------------------------------------------------------------------------------------------------------------------
 
 // ANGULAR f32, compile-time chunk count FULL (dim = 32*FULL + tail).  Query chunk values live in registers.
-// Rows are lane-permuted in HBM (see permute_rows_f32_kernel) so one LDG.128/64/32 per lane and group fetches a
-// lane's share of G*V chunks; all rows of a batch of 16 candidates are in flight before the first FMA.
+// Candidate rows are fetched with 1-D bulk copies (cp.async.bulk -> UBLKCP): lane b issues the copy of row b of the
+// batch into the staging tile and one mbarrier collects all completions, so a whole batch of rows is in flight with
+// one instruction per row and no data registers.  Rows are lane-permuted in HBM (permute_rows_f32_kernel) so that lane
+// i then reads its share of G*V chunks with conflict-free LDS.128/64/32.
 template <int FULL>
 struct DistF32 {
     static constexpr int V = (FULL % 4 == 0) ? 4 : ((FULL % 2 == 0) ? 2 : 1);
     static constexpr int G = FULL / V;
     static constexpr int NQ = FULL > 0 ? FULL : 1;
+    static constexpr bool kStaged = FULL > 0;
     float q[NQ];
 
     __device__ __forceinline__ void load_query(const DeviceIndex& ix, const WarpCtx& c) {
@@ -178,57 +216,48 @@ struct DistF32 {
         for (int ch = 0; ch < FULL; ++ch) q[ch] = c.qs[ch * 32 + c.lane];
     }
 
-    static __device__ __forceinline__ void load_row(const char* lane_base, uint32_t id, uint32_t stride_bytes,
-                                                    float (&d)[NQ]) {
-        const float* row = reinterpret_cast<const float*>(lane_base + (size_t)id * stride_bytes);  // IMAD.WIDE.U32
+    __device__ __forceinline__ float partial(const unsigned char* row) const {
+        const float* r = reinterpret_cast<const float*>(row);
+        float p = 0.0f;
 #pragma unroll
         for (int g = 0; g < G; ++g) {
             if (V == 4) {
-                const float4 v = ldg_row_f4(row + g * 128);
-                d[g * 4 + 0] = v.x;
-                d[g * 4 + 1] = v.y;
-                d[g * 4 + 2] = v.z;
-                d[g * 4 + 3] = v.w;
+                const float4 v = *reinterpret_cast<const float4*>(r + g * 128);
+                p = __fmaf_rn(v.x, q[g * 4 + 0], p);
+                p = __fmaf_rn(v.y, q[g * 4 + 1], p);
+                p = __fmaf_rn(v.z, q[g * 4 + 2], p);
+                p = __fmaf_rn(v.w, q[g * 4 + 3], p);
             } else if (V == 2) {
-                const float2 v = ldg_row_f2(row + g * 64);
-                d[g * 2 + 0] = v.x;
-                d[g * 2 + 1] = v.y;
+                const float2 v = *reinterpret_cast<const float2*>(r + g * 64);
+                p = __fmaf_rn(v.x, q[g * 2 + 0], p);
+                p = __fmaf_rn(v.y, q[g * 2 + 1], p);
             } else {
-                d[g] = ldg_row_f1(row + g * 32);
+                p = __fmaf_rn(r[g * 32], q[g], p);
             }
         }
+        return p;
     }
 
     __device__ __forceinline__ float dists(const DeviceIndex& ix, WarpCtx& c, uint32_t my_id, int k) {
         const uint32_t stride_bytes = ix.row_stride * 4u;
         if (FULL > 0) {
-            const char* lane_base = static_cast<const char*>(ix.vectors) + c.lane * (V * 4);
-            for (int j0 = 0; j0 < k; j0 += 16) {
-                float data[16][NQ];
-                // 4 groups of 4 rows; a group is skipped as a whole (uniform branch), inside a group indices past
-                // the end re-load the last candidate (same sectors) instead of predicating every instruction off.
+            const uint32_t copy_bytes = FULL * 128u;  // the permuted chunk part of a row (multiple of 16)
+            const int rb = (int)c.stg_rows;
+            for (int j0 = 0; j0 < k; j0 += rb) {
+                const int nb = (k - j0) < rb ? (k - j0) : rb;
+                const uint32_t id = __shfl_sync(kFullMask, my_id, (j0 + c.lane) & 31);
+                __syncwarp();  // everyone is done reading the previous batch
+                if (c.lane == 0) mbar_arrive_expect_tx(c.bar, (uint32_t)nb * copy_bytes);
+                if (c.lane < nb)
+                    bulk_copy_g2s(smem_u32(c.stg) + c.lane * copy_bytes,
+                                  static_cast<const char*>(ix.vectors) + (size_t)id * stride_bytes, copy_bytes, c.bar);
+                mbar_wait(c.bar, c.phase);
+                c.phase ^= 1u;
+                const unsigned char* mine = c.stg + c.lane * (V * 4);
+                for (int b = 0; b < nb; b += 4) {  // rows past nb hold stale data: computed, never used
 #pragma unroll
-                for (int g4 = 0; g4 < 4; ++g4) {
-                    if (j0 + g4 * 4 < k) {
-#pragma unroll
-                        for (int b = 0; b < 4; ++b) {
-                            const int idx = j0 + g4 * 4 + b;
-                            const uint32_t id = __shfl_sync(kFullMask, my_id, idx < k ? idx : k - 1);
-                            load_row(lane_base, id, stride_bytes, data[g4 * 4 + b]);
-                        }
-                    }
-                }
-#pragma unroll
-                for (int g4 = 0; g4 < 4; ++g4) {
-                    if (j0 + g4 * 4 < k) {
-#pragma unroll
-                        for (int b = 0; b < 4; ++b) {
-                            float p = 0.0f;
-#pragma unroll
-                            for (int ch = 0; ch < FULL; ++ch) p = __fmaf_rn(data[g4 * 4 + b][ch], q[ch], p);
-                            c.tile[(j0 + g4 * 4 + b) * kTileStride + c.lane] = p;
-                        }
-                    }
+                    for (int u = 0; u < 4; ++u)
+                        c.tile[(j0 + b + u) * kTileStride + c.lane] = partial(mine + (b + u) * copy_bytes);
                 }
             }
             __syncwarp();
@@ -263,6 +292,7 @@ struct DistF32 {
 
 // ANGULAR f32, any dim (runtime chunk count; natural row layout; query read from shared memory).
 struct DistF32Generic {
+    static constexpr bool kStaged = false;
     __device__ __forceinline__ void load_query(const DeviceIndex&, const WarpCtx&) {}
     __device__ __forceinline__ float dists(const DeviceIndex& ix, WarpCtx& c, uint32_t my_id, int k) {
         const float* base = static_cast<const float*>(ix.vectors);
@@ -295,6 +325,7 @@ struct DistF32Generic {
 // ANGULAR_INT i8: exact i32 r, dx via dp4a (src/math.rs:59-89), then 1 - r/(sqrt(dx)*sqrt(dy)) in IEEE f32
 // (src/elements/angular_int.rs:47-59).  Rows and the query are zero-padded to row_stride bytes.
 struct DistI8 {
+    static constexpr bool kStaged = false;
     __device__ __forceinline__ void load_query(const DeviceIndex&, const WarpCtx&) {}
     __device__ __forceinline__ float dists(const DeviceIndex& ix, WarpCtx& c, uint32_t my_id, int k) {
         const int8_t* base = static_cast<const int8_t*>(ix.vectors);
@@ -336,6 +367,7 @@ struct DistI8 {
 // EMBEDDINGS: element = ordered sum of embedding rows, normalised, then the f32 angular distance
 // (src/elements/embeddings/mod.rs:124-143,164-174; src/math.rs:92-150).  Natural row layout, runtime dim.
 struct DistSum {
+    static constexpr bool kStaged = false;
     __device__ __forceinline__ void load_query(const DeviceIndex&, const WarpCtx&) {}
 
     // materialises ElementContainer::get(id) into c.xs (all lanes participate)
@@ -637,17 +669,27 @@ __device__ __forceinline__ void search_layer(const DeviceIndex& ix, WarpCtx& c, 
 //     the move itself goes through registers (read everything, sync, write), so it is race free in place.
 // The cost of an expansion no longer depends on how many keys pass.  `hist` aliases the distance tile (free here).
 // ------------------------------------------------------------------------------------------------------------------
+__host__ __device__ constexpr uint32_t fast_list_pow2(int R) {
+    uint32_t p = 32;
+    while (p <= 32u * (uint32_t)R) p <<= 1;
+    return p;
+}
+// bytes of shared memory the fast list needs: Ld[P] + Li[32*R]
+__host__ __device__ constexpr uint32_t fast_list_bytes(int R) { return (fast_list_pow2(R) + 32u * (uint32_t)R) * 4u; }
+
 template <class Dist, int R>
 __device__ __forceinline__ void search_layer_fast(const DeviceIndex& ix, WarpCtx& c, Dist& dist, const uint32_t* rows,
                                                   const uint32_t width, const uint32_t entrypoint, const uint32_t ef,
                                                   const uint32_t vis_slots, uint32_t* out_n) {
     constexpr uint32_t cap = 32u * R;
+    constexpr uint32_t P = fast_list_pow2(R);  // Ld is padded to a power of two > cap with +inf-like sentinels
     constexpr uint32_t kFlag = 0x80000000u, kDMask = 0x7FFFFFFFu;
     uint32_t* Ld = reinterpret_cast<uint32_t*>(c.list);
-    uint32_t* Li = Ld + cap;
+    uint32_t* Li = Ld + P;
     uint32_t* hist = reinterpret_cast<uint32_t*>(c.tile);  // cap + 1 counters
     const int lane = c.lane;
     for (uint32_t i = lane; i < vis_slots; i += 32) c.visited[i] = kUnusedId;
+    for (uint32_t i = lane; i < P; i += 32) Ld[i] = kDMask;  // sentinel: larger than any distance, never flagged
     __syncwarp();
     const uint32_t vis_limit = vis_slots - (vis_slots >> 3);
     uint32_t vis_count = 1;
@@ -756,18 +798,12 @@ __device__ __forceinline__ void search_layer_fast(const DeviceIndex& ix, WarpCtx
 #pragma unroll
             for (int t = 0; t < R; ++t) hist[R * lane + t] = 0;
             if (lane == 0) hist[cap] = 0;
-            // rank of my key among the entries: lower bound on the distance, refined by id on exact ties
-            uint32_t lo = 0, hi = n;
-            for (int it = 32 - __clz(n); it > 0; --it) {
-                const uint32_t mid = (lo + hi) >> 1;
-                const uint32_t v = Ld[mid < n ? mid : n - 1] & kDMask;
-                if (lo < hi) {
-                    if (v < my_d)
-                        lo = mid + 1;
-                    else
-                        hi = mid;
-                }
-            }
+            // rank of my key among the entries: branch-free lower bound on the distance over the padded array
+            // (entries at positions >= n are sentinels), refined by id on exact distance ties
+            uint32_t lo = 0;
+#pragma unroll
+            for (uint32_t step = P / 2; step >= 1; step >>= 1)
+                if ((Ld[lo + step - 1] & kDMask) < my_d) lo += step;
             while (lo < n && (Ld[lo] & kDMask) == my_d && Li[lo] < my_id) ++lo;  // (d, id) tuple order
             const uint32_t rank_l = lo;
             __syncwarp();
@@ -808,12 +844,11 @@ __device__ __forceinline__ void search_layer_fast(const DeviceIndex& ix, WarpCtx
             uint32_t before = (pass && rank_l > 0) ? hist[rank_l - 1] : 0;
             const unsigned peers = __match_any_sync(kFullMask, pass ? rank_l : (0x80000000u | lane));
             const unsigned multi = __ballot_sync(kFullMask, pass && (peers & (peers - 1)));
-            for (unsigned t = multi; t; t &= t - 1) {
+            for (unsigned t = multi; t; t &= t - 1) {  // keys that share a gap with another key: order them
                 const int j = __ffs(t) - 1;
-                const uint32_t rj = __shfl_sync(kFullMask, rank_l, j);
                 const uint32_t dj = __shfl_sync(kFullMask, my_d, j);
                 const uint32_t ij = __shfl_sync(kFullMask, my_id, j);
-                if (pass && j != lane && rj == rank_l && (dj < my_d || (dj == my_d && ij < my_id))) before += 1;
+                if (((peers >> j) & 1u) && (dj < my_d || (dj == my_d && ij < my_id))) before += 1;
             }
             const uint32_t new_pos = rank_l + before;
             const uint32_t total = n + m;
@@ -955,20 +990,33 @@ __device__ __forceinline__ void prepare_query(const DeviceIndex& ix, const Searc
 // R == 0: generic list (64-bit keys, any capacity, shared or global memory) — the slow pass and very large max_search.
 // R  > 0: fast list with capacity 32*R for the bottom layer (upper layers always use R = 1).
 template <class Dist, int R>
-__global__ void __launch_bounds__(32) search_kernel(const DeviceIndex ix, const SearchArgs a) {
+__global__ void __launch_bounds__(32, R > 0 ? 16 : 1) search_kernel(const DeviceIndex ix, const SearchArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WarpCtx c;
     c.lane = threadIdx.x;
-    // shared layout: tile + id scratch | qs | xs | list | visited   (list/visited live in global memory on the slow path)
+    // shared layout: tile + id scratch | mbarrier | qs | xs | staging | list      (fast pass: visited set in global)
+    //                                                          ... | list | visited (generic pass, slow_pass == 0)
     unsigned char* sp = smem_raw;
     c.tile = reinterpret_cast<float*>(sp);
     c.ids = reinterpret_cast<uint32_t*>(sp + 32 * kTileStride * sizeof(float));
     sp += kTileBytes;
+    c.bar = smem_u32(sp);
+    c.phase = 0;
+    sp += 16;
     const uint32_t qbytes = (ix.kind == kAngularI8) ? ix.row_stride : ((ix.dim + 3u) & ~3u) * 4u;
     c.qs = reinterpret_cast<float*>(sp);
     sp += (qbytes + 15u) & ~15u;
     c.xs = reinterpret_cast<float*>(sp);
     if (ix.kind == kSumEmbeddings) sp += (qbytes + 15u) & ~15u;
+    c.stg = nullptr;
+    c.stg_rows = a.stg_rows;
+    if (Dist::kStaged) {
+        sp = smem_raw + (((size_t)(sp - smem_raw) + 127u) & ~(size_t)127u);
+        c.stg = sp;
+        sp += (size_t)a.stg_rows * ix.full * 128u;
+        if (c.lane == 0) mbar_init(c.bar, 1);
+        __syncwarp();
+    }
     uint32_t list_cap, vis_slots, vis_upper;
     if (a.slow_pass) {
         c.list = a.slow_list + (size_t)blockIdx.x * a.slow_list_cap;
@@ -978,11 +1026,15 @@ __global__ void __launch_bounds__(32) search_kernel(const DeviceIndex ix, const 
         vis_upper = a.slow_vis_slots;
     } else {
         c.list = reinterpret_cast<unsigned long long*>(sp);
-        sp += (size_t)a.list_cap * sizeof(unsigned long long);
-        c.visited = reinterpret_cast<uint32_t*>(sp);
         list_cap = a.list_cap;
         vis_slots = a.vis_slots;
         vis_upper = a.vis_slots_upper;
+        if (R > 0) {
+            c.visited = a.vis_global + (size_t)blockIdx.x * a.vis_slots;
+        } else {
+            sp += (size_t)a.list_cap * sizeof(unsigned long long);
+            c.visited = reinterpret_cast<uint32_t*>(sp);
+        }
     }
     Dist dist;
 
@@ -1054,14 +1106,14 @@ __global__ void __launch_bounds__(32) search_kernel(const DeviceIndex ix, const 
                     if (c.status) break;
                     uint32_t ep = 0;  // res[0] (capacity 32: a single row)
                     const unsigned m = __ballot_sync(kFullMask, ((uint32_t)c.lane < n) && (Ld[c.lane] >> 31));
-                    if (m) ep = Ld[32 + __ffs(m) - 1];  // Li = Ld + 32 for R = 1
+                    if (m) ep = Ld[fast_list_pow2(1) + __ffs(m) - 1];  // Li = Ld + P for R = 1
                     entrypoint = ep;
                 }
                 if (c.status == 0)
                     search_layer_fast<Dist, RB>(ix, c, dist, ix.layer_rows[bl], ix.layer_width[bl], entrypoint,
                                                 a.max_search, vis_slots, &n);
                 if (c.status == 0) {
-                    const uint32_t* Li = Ld + 32u * RB;
+                    const uint32_t* Li = Ld + fast_list_pow2(RB);
                     const uint32_t limit = a.max_search < k ? a.max_search : k;
                     uint32_t cnt = 0;
                     for (uint32_t base = 0; base < n && cnt < limit; base += 32) {
