@@ -153,7 +153,7 @@ struct WarpCtx {
     int lane;
     int status;
     int q_norm_i8;     // ANGULAR_INT: dy = sum q^2
-    uint32_t n_dist, n_expand, n_nbr;
+    uint32_t n_dist, n_expand, n_nbr, n_ins;
 };
 
 // ---- mbarrier + 1-D bulk copy (TMA, UBLKCP) helpers ----------------------------------------------------------------
@@ -442,6 +442,67 @@ __device__ __forceinline__ bool vis_insert(uint32_t* tab, uint32_t slots, uint32
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// Bucketed visited set for the fast pass (global memory, private to one warp): buckets of 8 u32 slots = one 32-byte
+// sector, filled from slot 0 upwards, 0xFFFFFFFF = empty.  A lookup is ONE sector read per lane (two 128-bit loads
+// that bypass L1); ids that are not found are inserted with plain stores — no atomics are needed because the table
+// has a single writer warp and conflicts between lanes of that warp are resolved in registers with match.any.
+// Returns true in lanes whose id was newly inserted.  Sets *overflow when a home bucket is full (-> slow path).
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 ldcg_u4(const uint32_t* p) {
+    uint4 v;
+    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ bool vis_bucket_insert(uint32_t* tab, uint32_t nbuckets, uint32_t id, bool valid,
+                                                  bool* overflow) {
+    uint32_t b = __umulhi(id * 0x9E3779B1u, nbuckets);
+    bool pending = valid, is_new = false;
+    for (int probe = 0;; ++probe) {
+        uint32_t* bucket = tab + (size_t)b * 8u;
+        uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
+        if (pending) {
+            lo = ldcg_u4(bucket);
+            hi = ldcg_u4(bucket + 4);
+        }
+        const bool found = (lo.x == id) | (lo.y == id) | (lo.z == id) | (lo.w == id) | (hi.x == id) |
+                           (hi.y == id) | (hi.z == id) | (hi.w == id);
+        // slots are filled in order, so the number of used slots is the index of the first empty one
+        const uint32_t used = (lo.x != kUnusedId) + (lo.y != kUnusedId) + (lo.z != kUnusedId) +
+                              (lo.w != kUnusedId) + (hi.x != kUnusedId) + (hi.y != kUnusedId) +
+                              (hi.z != kUnusedId) + (hi.w != kUnusedId);
+        if (pending && found) pending = false;
+        bool ins = pending && used < 8u;
+        const unsigned ins_mask = __ballot_sync(kFullMask, ins);
+        if (ins_mask) {
+            // the same id twice in one neighbour list (MultiSetVector allows duplicates): only the first lane inserts
+            const unsigned same_id = __match_any_sync(kFullMask, id) & ins_mask;
+            if (ins && (same_id & lanemask_lt())) {
+                ins = false;
+                pending = false;
+            }
+            // new ids that share a bucket take consecutive free slots
+            const unsigned same_b = __match_any_sync(kFullMask, b) & __ballot_sync(kFullMask, ins);
+            if (ins) {
+                const uint32_t slot = used + __popc(same_b & lanemask_lt());
+                if (slot < 8u) {
+                    __stcg(bucket + slot, id);
+                    is_new = true;
+                    pending = false;
+                }
+            }
+        }
+        if (pending) b = (b + 1 == nbuckets) ? 0 : b + 1;  // bucket full: continue in the next one
+        __syncwarp();
+        if (!__any_sync(kFullMask, pending)) break;
+        if (probe >= 64) {
+            *overflow = true;
+            break;
+        }
+    }
+    return is_new;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // search_for_neighbors (src/index/mod.rs:999-1037) on one layer.  On return the list holds the merged state;
 // *out_n is its length.  The result set (`res.into_sorted_vec()`) is the first min(|E|, ef) expanded entries.
 //
@@ -663,11 +724,12 @@ __device__ __forceinline__ void search_layer(const DeviceIndex& ix, WarpCtx& c, 
 // search_for_neighbors, fast variant: same state machine as search_layer (above) with a cheaper list representation.
 //   * keys are split into two u32 arrays in shared memory: Ld[j] = distance bits | expanded flag (bit 31) and
 //     Li[j] = id, sorted by (distance, id); capacity is 32*R (R compile time, odd -> conflict-free lane-major access);
-//   * all passing keys of one expansion are merged in one pass: every lane binary-searches the rank of its key, a
-//     shared-memory histogram of the ranks is prefix-summed with lane-major ownership (lane l owns positions
-//     [R*l, R*l+R)), which yields for every existing entry how far it moves and for every new key where it lands;
-//     the move itself goes through registers (read everything, sync, write), so it is race free in place.
-// The cost of an expansion no longer depends on how many keys pass.  `hist` aliases the distance tile (free here).
+//     Ld is padded to a power of two with sentinels so the rank search is a branch-free lower bound;
+//   * all passing keys of one expansion are merged in one pass: every lane finds the rank of its key, then each lane
+//     (owning positions [R*l, R*l+R)) counts how many new keys land at or before each of its entries and moves them
+//     through registers (read everything, sync, write), so the merge is race free in place;
+//   * keys strictly farther than the tail of a full list are dropped up front (they can never matter);
+//   * the visited set is the bucketed global-memory table (vis_bucket_insert): one sector read per neighbour.
 // ------------------------------------------------------------------------------------------------------------------
 __host__ __device__ constexpr uint32_t fast_list_pow2(int R) {
     uint32_t p = 32;
@@ -686,12 +748,16 @@ __device__ __forceinline__ void search_layer_fast(const DeviceIndex& ix, WarpCtx
     constexpr uint32_t kFlag = 0x80000000u, kDMask = 0x7FFFFFFFu;
     uint32_t* Ld = reinterpret_cast<uint32_t*>(c.list);
     uint32_t* Li = Ld + P;
-    uint32_t* hist = reinterpret_cast<uint32_t*>(c.tile);  // cap + 1 counters
     const int lane = c.lane;
-    for (uint32_t i = lane; i < vis_slots; i += 32) c.visited[i] = kUnusedId;
+    const uint32_t nbuckets = vis_slots >> 3;
+    {
+        uint4* v4 = reinterpret_cast<uint4*>(c.visited);
+        const uint4 e = make_uint4(kUnusedId, kUnusedId, kUnusedId, kUnusedId);
+        for (uint32_t i = lane; i < nbuckets * 2; i += 32) __stcg(v4 + i, e);
+    }
     for (uint32_t i = lane; i < P; i += 32) Ld[i] = kDMask;  // sentinel: larger than any distance, never flagged
     __syncwarp();
-    const uint32_t vis_limit = vis_slots - (vis_slots >> 3);
+    const uint32_t vis_limit = vis_slots - (vis_slots >> 2);  // keep the bucket load factor <= 3/4
     uint32_t vis_count = 1;
 
     {
@@ -702,24 +768,27 @@ __device__ __forceinline__ void search_layer_fast(const DeviceIndex& ix, WarpCtx
             *out_n = 0;
             return;
         }
+        bool ovf = false;
+        vis_bucket_insert(c.visited, nbuckets, entrypoint, lane == 0, &ovf);
         if (lane == 0) {
             Ld[0] = __float_as_uint(d0);
             Li[0] = entrypoint;
-            vis_insert(c.visited, vis_slots, entrypoint);
         }
         __syncwarp();
     }
     uint32_t n = 1, n_exp = 0, cursor = 0, pos_thr = 0, thr_bits = 0;
 
     while (true) {
-        // ---- pq.pop() ----
+        // ---- pq.pop(): first unexpanded entry at or after the cursor; also find the runner-up ----
         int px = -1;
-        for (uint32_t base = cursor & ~31u; base < n; base += 32) {
-            const uint32_t j = base + lane;
+        uint32_t base_sel = cursor & ~31u;
+        unsigned sel_mask = 0;
+        for (; base_sel < n; base_sel += 32) {
+            const uint32_t j = base_sel + lane;
             const bool un = (j < n) && (j >= cursor) && !(Ld[j] & kFlag);
-            const unsigned m = __ballot_sync(kFullMask, un);
-            if (m) {
-                px = base + __ffs(m) - 1;
+            sel_mask = __ballot_sync(kFullMask, un);
+            if (sel_mask) {
+                px = base_sel + __ffs(sel_mask) - 1;
                 break;
             }
         }
@@ -727,6 +796,16 @@ __device__ __forceinline__ void search_layer_fast(const DeviceIndex& ix, WarpCtx
         const uint32_t xd = Ld[px];  // unflagged
         const uint32_t xid = Li[px];
         if (n_exp >= ef && xd > thr_bits) break;
+        // warm L2 with the adjacency row of the most likely next expansion (the runner-up in the same 32-entry row)
+        {
+            const unsigned rest = sel_mask & (sel_mask - 1);
+            if (rest) {
+                const uint32_t yid = Li[base_sel + __ffs(rest) - 1];
+                if ((uint32_t)lane * 32u < width * 4u)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(rows + (size_t)yid * width) +
+                                                                  lane * 32));
+            }
+        }
 
         // ---- res.push ----
         __syncwarp();
@@ -768,16 +847,17 @@ __device__ __forceinline__ void search_layer_fast(const DeviceIndex& ix, WarpCtx
             const unsigned vm = __ballot_sync(kFullMask, valid);
             if (vm == 0) break;
             c.n_nbr += __popc(vm);
-            const bool is_new = valid && vis_insert(c.visited, vis_slots, nb);
+            bool ovf = false;
+            const bool is_new = vis_bucket_insert(c.visited, nbuckets, nb, valid, &ovf);
             const unsigned nm = __ballot_sync(kFullMask, is_new);
             const int k = __popc(nm);
-            if (k == 0) continue;
             vis_count += k;
-            if (vis_count > vis_limit) {
+            if (__any_sync(kFullMask, ovf) || vis_count > vis_limit) {
                 c.status |= kStatusOverflow;
                 *out_n = n;
                 return;
             }
+            if (k == 0) continue;
             if (is_new) c.ids[__popc(nm & lanemask_lt())] = nb;
             __syncwarp();
             const uint32_t my_id = c.ids[lane < k ? lane : 0];
@@ -789,15 +869,16 @@ __device__ __forceinline__ void search_layer_fast(const DeviceIndex& ix, WarpCtx
                 return;
             }
             const uint32_t my_d = __float_as_uint(d);
-            const bool pass = (lane < k) && (n_exp < ef || my_d < thr_bits);
+            // !res.is_full() || distance < res.peek().0   (:1029)
+            bool pass = (lane < k) && (n_exp < ef || my_d < thr_bits);
+            // a key strictly farther than the last entry of a full list has >= ef strictly closer entries before
+            // it (cap > ef): it can never be expanded nor reported, so it need not enter the list at all
+            if (n == cap) pass = pass && !(my_d > (Ld[cap - 1] & kDMask));
             const unsigned pm = __ballot_sync(kFullMask, pass);
             if (pm == 0) continue;
             const uint32_t m = __popc(pm);
+            c.n_ins += m;
 
-            // zero the histogram (lane-major) while the binary search runs
-#pragma unroll
-            for (int t = 0; t < R; ++t) hist[R * lane + t] = 0;
-            if (lane == 0) hist[cap] = 0;
             // rank of my key among the entries: branch-free lower bound on the distance over the padded array
             // (entries at positions >= n are sentinels), refined by id on exact distance ties
             uint32_t lo = 0;
@@ -806,87 +887,60 @@ __device__ __forceinline__ void search_layer_fast(const DeviceIndex& ix, WarpCtx
                 if ((Ld[lo + step - 1] & kDMask) < my_d) lo += step;
             while (lo < n && (Ld[lo] & kDMask) == my_d && Li[lo] < my_id) ++lo;  // (d, id) tuple order
             const uint32_t rank_l = lo;
-            __syncwarp();
-            if (pass) atomicAdd(hist + rank_l, 1u);
-            __syncwarp();
-            // inclusive prefix over the histogram, lane-major: sh(j) = number of new keys ranked at or before entry j
-            uint32_t pre[R];
-            uint32_t run = 0;
-#pragma unroll
-            for (int t = 0; t < R; ++t) {
-                run += hist[R * lane + t];
-                pre[t] = run;
-            }
-            uint32_t incl = run;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t v = __shfl_up_sync(kFullMask, incl, o);
-                if (lane >= o) incl += v;
-            }
-            const uint32_t offset = incl - run;
-            // read my entries into registers, publish the prefix sums (for the new keys' positions)
-            uint32_t dv[R], iv[R];
+            // my entries (lane-major: lane l owns positions [R*l, R*l+R)) and how far each one moves:
+            // sh(j) = number of new keys ranked at or before entry j;  my key lands at rank_l + #smaller new keys
+            uint32_t dv[R], iv[R], sh[R];
 #pragma unroll
             for (int t = 0; t < R; ++t) {
                 const uint32_t j = R * lane + t;
-                dv[t] = 0;
-                iv[t] = 0;
-                if (j < n) {
-                    dv[t] = Ld[j];
-                    iv[t] = Li[j];
-                }
+                dv[t] = Ld[j];  // positions >= n hold sentinels (Ld is padded), Li is only read below n
+                iv[t] = j < n ? Li[j] : 0u;
+                sh[t] = 0;
             }
-            __syncwarp();
-#pragma unroll
-            for (int t = 0; t < R; ++t) hist[R * lane + t] = offset + pre[t];
-            __syncwarp();
-            // position of my key: its rank + the new keys ranked before it (+ order among keys of the same gap)
-            uint32_t before = (pass && rank_l > 0) ? hist[rank_l - 1] : 0;
-            const unsigned peers = __match_any_sync(kFullMask, pass ? rank_l : (0x80000000u | lane));
-            const unsigned multi = __ballot_sync(kFullMask, pass && (peers & (peers - 1)));
-            for (unsigned t = multi; t; t &= t - 1) {  // keys that share a gap with another key: order them
+            uint32_t rank_n = 0;
+            for (unsigned t = pm; t; t &= t - 1) {
                 const int j = __ffs(t) - 1;
+                const uint32_t rj = __shfl_sync(kFullMask, rank_l, j);
                 const uint32_t dj = __shfl_sync(kFullMask, my_d, j);
                 const uint32_t ij = __shfl_sync(kFullMask, my_id, j);
-                if (((peers >> j) & 1u) && (dj < my_d || (dj == my_d && ij < my_id))) before += 1;
+                rank_n += (dj < my_d || (dj == my_d && ij < my_id)) ? 1u : 0u;
+#pragma unroll
+                for (int tt = 0; tt < R; ++tt) sh[tt] += (rj <= (uint32_t)(R * lane + tt)) ? 1u : 0u;
             }
-            const uint32_t new_pos = rank_l + before;
+            const uint32_t new_pos = rank_l + rank_n;
             const uint32_t total = n + m;
-            uint32_t drop_min = 0xFFFFFFFFu, drop_flagged = 0;
+            uint32_t drop_flagged = 0;
+            __syncwarp();  // every lane holds its entries in registers: the list can be rewritten in place
 #pragma unroll
             for (int t = 0; t < R; ++t) {
                 const uint32_t j = R * lane + t;
-                const uint32_t sh = offset + pre[t];
-                if (j < n && sh > 0) {
-                    const uint32_t np = j + sh;
+                if (j < n && sh[t] > 0) {
+                    const uint32_t np = j + sh[t];
                     if (np < cap) {
                         Ld[np] = dv[t];
                         Li[np] = iv[t];
                     } else {
-                        drop_min = min(drop_min, dv[t] & kDMask);
                         drop_flagged += dv[t] >> 31;
                     }
                 }
             }
-            if (pass) {
-                if (new_pos < cap) {
-                    Ld[new_pos] = my_d;
-                    Li[new_pos] = my_id;
-                } else {
-                    drop_min = min(drop_min, my_d);
-                }
+            if (pass && new_pos < cap) {
+                Ld[new_pos] = my_d;
+                Li[new_pos] = my_id;
             }
             __syncwarp();
             if (total > cap) {
-                drop_min = warp_min_u32(kFullMask, drop_min);
                 n = cap;
-                if (!((Ld[ef - 1] & kDMask) < drop_min)) {
+                // entries fell off the end: legal only if >= ef strictly closer entries remain; everything dropped is
+                // >= the last kept entry, so "L[ef-1].d < L[cap-1].d" is sufficient (else: slow path)
+                if (!((Ld[ef - 1] & kDMask) < (Ld[cap - 1] & kDMask))) {
                     c.status |= kStatusOverflow;
                     *out_n = n;
                     return;
                 }
                 if (n_exp >= ef) {
                     if (pos_thr + m >= cap) {
+                        // res.peek() itself left L: res now spans evicted entries ("not full" regime); recount
                         uint32_t cnt = 0;
                         for (uint32_t base = 0; base < n; base += 32) {
                             const uint32_t j = base + lane;
@@ -1046,7 +1100,7 @@ __global__ void __launch_bounds__(32, R > 0 ? 16 : 1) search_kernel(const Device
         if (a.slow_pass && a.query_status[qi] != kStatusOverflow) continue;  // only flagged queries
 
         c.status = 0;
-        c.n_dist = c.n_expand = c.n_nbr = 0;
+        c.n_dist = c.n_expand = c.n_nbr = c.n_ins = 0;
         c.q_norm_i8 = 0;
         prepare_query(ix, a, c, qi);
         dist.load_query(ix, c);
@@ -1156,7 +1210,7 @@ __global__ void __launch_bounds__(32, R > 0 ? 16 : 1) search_kernel(const Device
                 a.out_stats[qi * 4 + 0] = c.n_dist;
                 a.out_stats[qi * 4 + 1] = c.n_expand;
                 a.out_stats[qi * 4 + 2] = c.n_nbr;
-                a.out_stats[qi * 4 + 3] = a.slow_pass ? 1ull : 0ull;
+                a.out_stats[qi * 4 + 3] = (a.slow_pass ? 1ull : 0ull) | ((unsigned long long)c.n_ins << 8);
             }
             if (!(c.status & kStatusOverflow)) a.query_status[qi] = 0;
         }
