@@ -58,6 +58,16 @@ def load_library():
         "granne_b200_merge_topk_device": (i32, [i32, vp, vp, vp, sz, sz, u32, vp, vp, vp]),
         "granne_b200_inspect_index": (i32, [vp, sz, vp, vp, vp, vp, sz]),
         "granne_b200_decode_layer": (i32, [vp, sz, u64, vp, sz]),
+        "granne_b200_build_config_default": (None, [vp]),
+        "granne_b200_builder_new": (i32, [vp, i32, vp, sz, vp, sz, i32, C.POINTER(vp)]),
+        "granne_b200_builder_build": (i32, [vp, u64]),
+        "granne_b200_builder_len": (u64, [vp]),
+        "granne_b200_builder_num_layers": (u64, [vp]),
+        "granne_b200_builder_layer_len": (u64, [vp, u64]),
+        "granne_b200_builder_write_index": (i32, [vp, vp, sz, C.POINTER(sz)]),
+        "granne_b200_builder_get_index": (i32, [vp, C.POINTER(vp)]),
+        "granne_b200_builder_free": (None, [vp]),
+        "granne_b200_elements_from_raw": (i32, [i32, vp, u64, u32, i32, vp, sz, C.POINTER(sz)]),
         "granne_b200_launch_count": (u64, [vp]),
         "granne_b200_device_bytes": (u64, [vp]),
     }
@@ -237,6 +247,103 @@ class Granne:
 
     def device_bytes(self):
         return int(load_library().granne_b200_device_bytes(self._h))
+
+
+class BuildConfig(C.Structure):
+    """granne::BuildConfig (src/index/mod.rs:198-291) as the C ABI struct granne_b200_build_config."""
+    _fields_ = [("layer_multiplier", C.c_float), ("expected_num_elements", C.c_int64),
+                ("num_neighbors", C.c_uint32), ("max_search", C.c_uint32), ("reinsert_elements", C.c_int32),
+                ("show_progress", C.c_int32)]
+
+
+def elements_from_raw(element_type, raw, device=0):
+    """Builds an elements file image from raw f32 rows on the GPU exactly like `Vector::from(Vec<f32>)` per row
+    (normalise for "angular", quantise for "angular_int")."""
+    L = load_library()
+    raw = np.ascontiguousarray(raw, dtype=np.float32)
+    n, dim = raw.shape
+    kind = _kind(element_type)
+    need = C.c_size_t()
+    _check(L.granne_b200_elements_from_raw(kind, None, n, dim, device, None, 0, C.byref(need)))
+    out = np.empty(need.value, dtype=np.uint8)
+    _check(L.granne_b200_elements_from_raw(kind, _ptr(raw), n, dim, device, _ptr(out), out.size, C.byref(need)))
+    return out
+
+
+class GranneBuilder:
+    """granne.GranneBuilder (py/src/lib.rs:346-579; src/index/mod.rs:295-531) on the GPU.
+
+    GranneBuilder(element_type, elements_bytes, embeddings_bytes=None, num_neighbors=30, max_search=200,
+                  layer_multiplier=15.0, reinsert_elements=True, expected_num_elements=None, device=0)
+    `elements_bytes` is an elements file image (see elements_from_raw / Granne.save_elements)."""
+
+    def __init__(self, element_type, elements_bytes, embeddings_bytes=None, num_neighbors=30, max_search=200,
+                 layer_multiplier=15.0, reinsert_elements=True, expected_num_elements=None, show_progress=False,
+                 device=0):
+        L = load_library()
+        cfg = BuildConfig()
+        L.granne_b200_build_config_default(C.byref(cfg))
+        cfg.num_neighbors = num_neighbors
+        cfg.max_search = max_search
+        cfg.layer_multiplier = layer_multiplier
+        cfg.reinsert_elements = int(bool(reinsert_elements))
+        cfg.expected_num_elements = -1 if expected_num_elements is None else int(expected_num_elements)
+        cfg.show_progress = int(bool(show_progress))
+        eb = np.frombuffer(elements_bytes, dtype=np.uint8)
+        mb = np.frombuffer(embeddings_bytes, dtype=np.uint8) if embeddings_bytes is not None else None
+        h = C.c_void_p()
+        _check(L.granne_b200_builder_new(C.byref(cfg), _kind(element_type), _ptr(eb), eb.size,
+                                         _ptr(mb) if mb is not None else None, mb.size if mb is not None else 0,
+                                         device, C.byref(h)))
+        self._h = h
+        self.device = device
+
+    def build(self, num_elements=0):
+        """Builder::build() / build_partial(num_elements)."""
+        _check(load_library().granne_b200_builder_build(self._h, int(num_elements)))
+
+    def __len__(self):
+        return int(load_library().granne_b200_builder_len(self._h))
+
+    def num_layers(self):
+        return int(load_library().granne_b200_builder_num_layers(self._h))
+
+    def layer_len(self, layer):
+        return int(load_library().granne_b200_builder_layer_len(self._h, layer))
+
+    def index_bytes(self):
+        """Index::write_index into memory: a granne index file image."""
+        L = load_library()
+        need = C.c_size_t()
+        _check(L.granne_b200_builder_write_index(self._h, None, 0, C.byref(need)))
+        out = np.empty(need.value, dtype=np.uint8)
+        _check(L.granne_b200_builder_write_index(self._h, _ptr(out), out.size, C.byref(need)))
+        return out[:need.value]
+
+    def save_index(self, path):
+        """GranneBuilder.save_index(path) (py/src/lib.rs)."""
+        with open(path, "wb") as f:
+            f.write(self.index_bytes().tobytes())
+
+    def get_index(self):
+        """GranneBuilder::get_index: a searchable Granne sharing the staged elements."""
+        h = C.c_void_p()
+        _check(load_library().granne_b200_builder_get_index(self._h, C.byref(h)))
+        g = Granne.__new__(Granne)
+        g._h = h
+        g.device = self.device
+        return g
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load_library().granne_b200_builder_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def inspect_index(index_bytes):

@@ -6,6 +6,8 @@
 // src/odd_byte_int.rs:3-36).  Nothing here is shared with oracle/ (the oracle is test infrastructure).
 #pragma once
 
+#include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <string>
@@ -330,6 +332,133 @@ inline bool parse_sum_elements(const uint8_t* buf, size_t len, SumElements* out,
     out->terms.resize(nterms);
     for (uint64_t i = 0; i < nterms; ++i) out->terms[i] = static_cast<uint32_t>(load_le(data + 3 * i, 3));
     return true;
+}
+
+// ---- writers (Index::write_index, src/index/io.rs:11-70; set_vector.rs:117-148,169-221; offsets.rs:233-241) ----------
+
+// Stream VByte (scalar) encoder for one list of max(4, count) numbers; layout as read by decode_neighbor_list.
+inline void encode_vbyte(const uint32_t* nums, uint32_t n, std::vector<uint8_t>* out) {
+    const size_t nctrl = (n + 3) / 4;
+    const size_t base = out->size();
+    out->resize(base + nctrl, 0);
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t v = nums[i];
+        const int nb = v < (1u << 8) ? 1 : (v < (1u << 16) ? 2 : (v < (1u << 24) ? 3 : 4));
+        (*out)[base + (i >> 2)] |= static_cast<uint8_t>((nb - 1) << ((i & 3) * 2));
+        for (int b = 0; b < nb; ++b) out->push_back(static_cast<uint8_t>(v >> (8 * b)));
+    }
+}
+
+// set_encode (set_vector.rs:117-148): `ids` ascending; count byte, then vbyte deltas or raw u32 when not smaller.
+inline void encode_neighbor_list(const uint32_t* ids, uint32_t count, std::vector<uint8_t>* out) {
+    if (count > 255) count = 255;
+    uint32_t delta[256];
+    for (uint32_t i = 0; i < count; ++i) delta[i] = i ? ids[i] - ids[i - 1] : ids[i];
+    uint32_t n = count;
+    while (n < 4) delta[n++] = 0;
+    std::vector<uint8_t> enc;
+    encode_vbyte(delta, n, &enc);
+    out->push_back(static_cast<uint8_t>(count));
+    if (enc.size() >= 4u * count) {
+        for (uint32_t i = 0; i < count; ++i)
+            for (int b = 0; b < 4; ++b) out->push_back(static_cast<uint8_t>(delta[i] >> (8 * b)));
+    } else {
+        out->insert(out->end(), enc.begin(), enc.end());
+    }
+}
+
+// One layer blob from fixed-width rows (FixedWidthSliceVector::write_as_multi_set_vector, set_vector.rs:169-221).
+inline bool encode_layer(const uint32_t* rows, uint64_t num_nodes, uint32_t stride, std::vector<uint8_t>* out,
+                         std::string* err) {
+    const size_t bytes_for_offsets = (1 + num_nodes / kOffsetsPerChunk) * kChunkBytes;
+    const size_t base = out->size();
+    out->resize(base + 8 + bytes_for_offsets, 0xFF);
+    for (int b = 0; b < 8; ++b) (*out)[base + b] = static_cast<uint8_t>(static_cast<uint64_t>(bytes_for_offsets) >> (8 * b));
+    std::vector<uint64_t> offsets;
+    offsets.reserve(num_nodes + 1);
+    offsets.push_back(0);
+    std::vector<uint32_t> tmp;
+    uint64_t total = 0;
+    for (uint64_t i = 0; i < num_nodes; ++i) {
+        tmp.clear();
+        const uint32_t* row = rows + i * stride;
+        for (uint32_t k = 0; k < stride; ++k)
+            if (row[k] != kUnused) tmp.push_back(row[k]);  // predicate |&x| x != UNUSED (io.rs:33)
+        std::sort(tmp.begin(), tmp.end());
+        const size_t before = out->size();
+        encode_neighbor_list(tmp.data(), static_cast<uint32_t>(tmp.size()), out);
+        total += out->size() - before;
+        offsets.push_back(total);
+    }
+    // Offsets::push: chunks of 60 u16 deltas with a u64 `initial` (offsets.rs:148-241)
+    uint8_t* chunks = out->data() + base + 8;
+    const size_t num_chunks = bytes_for_offsets / kChunkBytes;
+    for (size_t c = 0; c < num_chunks; ++c) {
+        uint8_t* ch = chunks + c * kChunkBytes;
+        const size_t first = c * kOffsetsPerChunk;
+        const uint64_t initial = first < offsets.size() ? offsets[first] : 0;
+        for (int b = 0; b < 8; ++b) ch[b] = static_cast<uint8_t>(initial >> (8 * b));
+        uint64_t prev = initial;
+        for (size_t k = 0; k < kOffsetsPerChunk && first + k < offsets.size(); ++k) {
+            const uint64_t d = offsets[first + k] - prev;
+            if (d >= 0xFFFF) {
+                *err = "neighbour list too long for a u16 offset delta";
+                return false;
+            }
+            ch[8 + 2 * k] = static_cast<uint8_t>(d);
+            ch[8 + 2 * k + 1] = static_cast<uint8_t>(d >> 8);
+            prev = offsets[first + k];
+        }
+    }
+    return true;
+}
+
+struct LayerView {
+    const uint32_t* rows;
+    uint64_t num_nodes;
+    uint32_t stride;
+};
+
+// write_index (io.rs:11-70): 1 KiB "granne" + JSON header (serde_json's default map orders keys alphabetically),
+// then one MultiSetVector blob per layer.
+inline bool encode_index(const std::vector<LayerView>& layers, std::vector<uint8_t>* out, std::string* err) {
+    out->assign(kMetadataLen, static_cast<uint8_t>(' '));
+    std::vector<uint64_t> sizes, counts;
+    for (const LayerView& L : layers) {
+        const size_t before = out->size();
+        if (!encode_layer(L.rows, L.num_nodes, L.stride, out, err)) return false;
+        sizes.push_back(out->size() - before);
+        counts.push_back(L.num_nodes);
+    }
+    uint64_t num_neighbors = 0;  // degree of node 0 in the last layer (io.rs:20-24)
+    if (!layers.empty() && layers.back().num_nodes > 0)
+        for (uint32_t k = 0; k < layers.back().stride; ++k)
+            if (layers.back().rows[k] != kUnused) ++num_neighbors;
+    auto arr = [](const std::vector<uint64_t>& v) {
+        std::string s = "[";
+        for (size_t i = 0; i < v.size(); ++i) s += (i ? "," : "") + std::to_string(v[i]);
+        return s + "]";
+    };
+    const std::string meta = std::string("granne") + "{\"compressed\":true,\"granne_version\":\"0.5.2\",\"layer_counts\":" +
+                             arr(counts) + ",\"layer_sizes\":" + arr(sizes) + ",\"num_elements\":" +
+                             std::to_string(counts.empty() ? 0 : counts.back()) + ",\"num_layers\":" +
+                             std::to_string(layers.size()) + ",\"num_neighbors\":" + std::to_string(num_neighbors) +
+                             ",\"version\":2}";
+    if (meta.size() > kMetadataLen) {
+        *err = "metadata does not fit the 1024-byte header";
+        return false;
+    }
+    std::memcpy(out->data(), meta.data(), meta.size());
+    return true;
+}
+
+// compute_num_elements_in_layer (src/index/mod.rs:634-643)
+inline uint64_t num_elements_in_layer(uint64_t total, float layer_multiplier, uint64_t layer_idx) {
+    const double m = static_cast<double>(layer_multiplier);
+    const double e = std::floor(std::log(static_cast<double>(total)) / std::log(m)) - static_cast<double>(layer_idx);
+    const double v = std::ceil(static_cast<double>(total) / std::pow(m, e));
+    const uint64_t r = v <= 0 ? 0 : (v >= 1.8e19 ? ~0ull : static_cast<uint64_t>(v));
+    return r < total ? r : total;
 }
 
 }  // namespace granne_b200

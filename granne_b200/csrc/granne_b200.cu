@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "formats.hpp"
+#include "build_kernels.cuh"
 #include "search_kernels.cuh"
 
 namespace gb = granne_b200;
@@ -72,7 +73,7 @@ struct granne_b200_index {
     int num_sms = 0;
     size_t smem_optin = 0;
     gb::DeviceIndex dev{};
-    std::vector<void*> allocations;
+    std::vector<std::shared_ptr<void>> allocations;  // device memory (shared with builder snapshots)
     uint64_t device_bytes = 0;
     uint64_t index_len = 0;  // Index::len
     std::vector<uint32_t> layer_max_degree;
@@ -114,7 +115,7 @@ int dev_alloc(Handle* h, T** out, size_t count) {
     void* p = nullptr;
     const size_t bytes = std::max<size_t>(count * sizeof(T), 16);
     GB_CUDA(cudaMalloc(&p, bytes));
-    h->allocations.push_back(p);
+    h->allocations.emplace_back(p, [](void* q) { cudaFree(q); });
     h->device_bytes += bytes;
     *out = static_cast<T*>(p);
     return GRANNE_B200_OK;
@@ -173,27 +174,10 @@ int stage_dense(Handle* h, const uint8_t* host_rows, uint64_t nrows, uint32_t di
     return GRANNE_B200_OK;
 }
 
-int open_impl(const uint8_t* index_bytes, size_t index_len, int kind, const uint8_t* el, size_t el_len,
-              const uint8_t* emb, size_t emb_len, int device, Handle** out) {
-    if (!out) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "out handle pointer is null");
-    *out = nullptr;
-    if (!index_bytes || !el) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "index/elements buffer is null");
-    if (kind != GRANNE_B200_ANGULAR && kind != GRANNE_B200_ANGULAR_INT && kind != GRANNE_B200_EMBEDDINGS)
-        return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "Invalid element type");
-    if (kind == GRANNE_B200_EMBEDDINGS && !emb)
-        return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "embeddings buffer required for this element type");
-
-    std::unique_ptr<Handle> h(new Handle());
-    int rc = check_device(device, &h->num_sms, &h->smem_optin);
-    if (rc) return rc;
-    h->device = device;
-    GB_CUDA(cudaSetDevice(device));
-
+// Stages the element container (vectors / embedding table + element term lists) in HBM.
+int stage_elements(Handle* h, int kind, const uint8_t* el, size_t el_len, const uint8_t* emb, size_t emb_len) {
     std::string err;
-    gb::HostGraph graph;
-    if (!gb::parse_index(index_bytes, index_len, &graph, &err)) return fail(GRANNE_B200_ERR_FORMAT, err);
-    if (graph.layers.size() > (size_t)gb::kMaxLayers) return fail(GRANNE_B200_ERR_FORMAT, "too many layers");
-
+    int rc;
     gb::DeviceIndex& d = h->dev;
     d.kind = kind;
     if (kind == GRANNE_B200_EMBEDDINGS) {
@@ -204,13 +188,13 @@ int open_impl(const uint8_t* index_bytes, size_t index_len, int kind, const uint
         for (uint32_t t : se.terms)
             if (t >= ev.num) return fail(GRANNE_B200_ERR_FORMAT, "element refers to a missing embedding id");
         if (ev.dim > 4096) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "embeddings wider than 4096 are unsupported");
-        rc = stage_dense(h.get(), ev.data, ev.num, (uint32_t)ev.dim, false);
+        rc = stage_dense(h, ev.data, ev.num, (uint32_t)ev.dim, false);
         if (rc) return rc;
         d.num_elements = se.offsets.size() - 1;
         unsigned long long* doff = nullptr;
         uint32_t* dterms = nullptr;
-        if ((rc = dev_alloc(h.get(), &doff, se.offsets.size()))) return rc;
-        if ((rc = dev_alloc(h.get(), &dterms, se.terms.size()))) return rc;
+        if ((rc = dev_alloc(h, &doff, se.offsets.size()))) return rc;
+        if ((rc = dev_alloc(h, &dterms, se.terms.size()))) return rc;
         GB_CUDA(cudaMemcpy(doff, se.offsets.data(), se.offsets.size() * 8, cudaMemcpyHostToDevice));
         if (!se.terms.empty())
             GB_CUDA(cudaMemcpy(dterms, se.terms.data(), se.terms.size() * 4, cudaMemcpyHostToDevice));
@@ -221,11 +205,50 @@ int open_impl(const uint8_t* index_bytes, size_t index_len, int kind, const uint
         const bool i8 = kind == GRANNE_B200_ANGULAR_INT;
         if (!gb::parse_dense(el, el_len, i8 ? 1 : 4, &dv, &err)) return fail(GRANNE_B200_ERR_FORMAT, err);
         if (dv.dim > 16384) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "vectors wider than 16384 are unsupported");
-        rc = stage_dense(h.get(), dv.data, dv.num, (uint32_t)dv.dim, i8);
+        rc = stage_dense(h, dv.data, dv.num, (uint32_t)dv.dim, i8);
         if (rc) return rc;
         d.num_elements = dv.num;
     }
+    return GRANNE_B200_OK;
+}
 
+int check_open_args(const void* el, int kind, const void* emb) {
+    if (!el) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "elements buffer is null");
+    if (kind != GRANNE_B200_ANGULAR && kind != GRANNE_B200_ANGULAR_INT && kind != GRANNE_B200_EMBEDDINGS)
+        return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "Invalid element type");
+    if (kind == GRANNE_B200_EMBEDDINGS && !emb)
+        return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "embeddings buffer required for this element type");
+    return GRANNE_B200_OK;
+}
+
+void finish_handle(Handle* h) {
+    h->index_len = h->dev.num_layers ? h->dev.layer_len[h->dev.num_layers - 1] : 0;
+    // slow-path visited table: large enough for every node of the bottom layer (capped)
+    const uint64_t want = h->index_len + h->index_len / 7 + 1024;
+    h->slow_vis_slots = (uint32_t)std::min<uint64_t>(want, 16ull << 20);
+}
+
+int open_impl(const uint8_t* index_bytes, size_t index_len, int kind, const uint8_t* el, size_t el_len,
+              const uint8_t* emb, size_t emb_len, int device, Handle** out) {
+    if (!out) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "out handle pointer is null");
+    *out = nullptr;
+    if (!index_bytes) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "index buffer is null");
+    int rc = check_open_args(el, kind, emb);
+    if (rc) return rc;
+
+    std::unique_ptr<Handle> h(new Handle());
+    rc = check_device(device, &h->num_sms, &h->smem_optin);
+    if (rc) return rc;
+    h->device = device;
+    GB_CUDA(cudaSetDevice(device));
+
+    std::string err;
+    gb::HostGraph graph;
+    if (!gb::parse_index(index_bytes, index_len, &graph, &err)) return fail(GRANNE_B200_ERR_FORMAT, err);
+    if (graph.layers.size() > (size_t)gb::kMaxLayers) return fail(GRANNE_B200_ERR_FORMAT, "too many layers");
+    if ((rc = stage_elements(h.get(), kind, el, el_len, emb, emb_len))) return rc;
+
+    gb::DeviceIndex& d = h->dev;
     d.num_layers = (int)graph.layers.size();
     for (int l = 0; l < d.num_layers; ++l) {
         const gb::HostLayer& L = graph.layers[l];
@@ -239,10 +262,7 @@ int open_impl(const uint8_t* index_bytes, size_t index_len, int kind, const uint
         d.layer_len[l] = L.num_nodes;
         h->layer_max_degree.push_back(L.max_degree);
     }
-    h->index_len = d.num_layers ? graph.layers.back().num_nodes : 0;
-    // slow-path visited table: large enough for every node of the bottom layer (capped)
-    const uint64_t want = h->index_len + h->index_len / 7 + 1024;
-    h->slow_vis_slots = (uint32_t)std::min<uint64_t>(want, 16ull << 20);
+    finish_handle(h.get());
     *out = h.release();
     return GRANNE_B200_OK;
 }
@@ -550,6 +570,231 @@ int error_from_bits(int bits) {
     return GRANNE_B200_OK;
 }
 
+// ---- GranneBuilder (src/index/mod.rs:295-531, 645-960) on the device ---------------------------------------------
+struct DistDispatch {
+    // calls f.template run<Dist>() for the distance engine that serves `d` (same mapping as dispatch_search)
+    template <class F>
+    static int call(const gb::DeviceIndex& d, F&& f) {
+        switch (d.kind) {
+            case gb::kAngularI8: return f.template run<gb::DistI8>();
+            case gb::kSumEmbeddings: return f.template run<gb::DistSum>();
+            default: break;
+        }
+        if (d.vec_group == 1 && d.full > 4) return f.template run<gb::DistF32Generic>();
+        switch (d.full) {
+            case 0: return f.template run<gb::DistF32<0>>();
+            case 1: return f.template run<gb::DistF32<1>>();
+            case 2: return f.template run<gb::DistF32<2>>();
+            case 3: return f.template run<gb::DistF32<3>>();
+            case 4: return f.template run<gb::DistF32<4>>();
+            case 6: return f.template run<gb::DistF32<6>>();
+            case 8: return f.template run<gb::DistF32<8>>();
+            default: return f.template run<gb::DistF32Generic>();
+        }
+    }
+};
+
+struct LinkLaunch {
+    Handle* h;
+    gb::BuildArgs a;
+    size_t smem;
+    unsigned grid;
+    cudaStream_t stream;
+    bool prune;
+    template <class Dist>
+    int run() {
+        if (prune) {
+            auto k = gb::build_prune_kernel<Dist>;
+            GB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
+            k<<<grid, 32, smem, stream>>>(h->dev, a);
+        } else {
+            auto k = gb::build_link_kernel<Dist>;
+            GB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
+            k<<<grid, 32, smem, stream>>>(h->dev, a);
+        }
+        h->launches++;
+        GB_CUDA(cudaGetLastError());
+        return GRANNE_B200_OK;
+    }
+};
+
+}  // namespace
+
+struct granne_b200_builder {
+    std::unique_ptr<Handle> h;  // search view over the layers built so far (+ the one under construction)
+    granne_b200_build_config cfg{};
+    uint32_t stride = 0;  // physical row stride (node_width rounded up to 8)
+    std::vector<std::shared_ptr<void>> layer_mem;
+    Workspace* ws = nullptr;
+    // batch scratch
+    uint32_t* d_ids = nullptr;
+    uint32_t* d_cand_ids = nullptr;
+    float* d_cand_d = nullptr;
+    uint32_t* d_cand_cnt = nullptr;
+    int* d_locks = nullptr;
+    unsigned int* d_counter = nullptr;
+    size_t batch_cap = 0, cand_cap = 0, locks_cap = 0;
+};
+
+namespace {
+
+using Builder = granne_b200_builder;
+
+int builder_reserve(Builder* b, size_t batch, size_t ef, size_t nodes) {
+    if (batch > b->batch_cap || ef > b->cand_cap) {
+        cudaFree(b->d_ids);
+        cudaFree(b->d_cand_ids);
+        cudaFree(b->d_cand_d);
+        cudaFree(b->d_cand_cnt);
+        b->d_ids = nullptr, b->d_cand_ids = nullptr, b->d_cand_d = nullptr, b->d_cand_cnt = nullptr;
+        b->batch_cap = std::max(batch, b->batch_cap);
+        b->cand_cap = std::max(ef, b->cand_cap);
+        GB_CUDA(cudaMalloc(&b->d_ids, b->batch_cap * 4));
+        GB_CUDA(cudaMalloc(&b->d_cand_ids, b->batch_cap * b->cand_cap * 4));
+        GB_CUDA(cudaMalloc(&b->d_cand_d, b->batch_cap * b->cand_cap * 4));
+        GB_CUDA(cudaMalloc(&b->d_cand_cnt, b->batch_cap * 4));
+    }
+    if (nodes > b->locks_cap) {
+        cudaFree(b->d_locks);
+        b->d_locks = nullptr;
+        GB_CUDA(cudaMalloc(&b->d_locks, nodes * sizeof(int)));
+        b->locks_cap = nodes;
+    }
+    if (!b->d_counter) GB_CUDA(cudaMalloc(&b->d_counter, 16));
+    return GRANNE_B200_OK;
+}
+
+// index_elements (:716-802) for the layer at dev.layer_rows[num_layers-1]
+int builder_index_elements(Builder* b, uint32_t layer_m, uint32_t ef, uint64_t already, uint64_t num, bool reinsert) {
+    Handle* h = b->h.get();
+    gb::DeviceIndex& d = h->dev;
+    const int cur = d.num_layers - 1;
+    uint32_t* rows = const_cast<uint32_t*>(d.layer_rows[cur]);
+    cudaStream_t stream = b->ws->stream;
+    const LaunchPlan plan = make_plan(h, ef);
+    if (plan.smem == 0) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "max_search too large");
+    const uint64_t first = reinsert ? 0 : already;
+    const uint64_t total = num - first;
+    const size_t max_batch = 4096;
+    int rc = builder_reserve(b, max_batch, ef, num);
+    if (rc) return rc;
+    GB_CUDA(cudaMemsetAsync(b->d_locks, 0, num * sizeof(int), stream));
+    const size_t link_smem = plan.base_smem + (size_t)std::max<uint32_t>(ef, 40) * 8 + 4 * 32 * 4 + 64;
+    uint64_t pos = 0;
+    while (pos < total) {
+        // nodes already linked into this layer: a batch never exceeds 1/16 of them (its members do not see each other)
+        const uint64_t present = reinsert ? num : first + pos;
+        const uint64_t bsz = std::min<uint64_t>(std::min<uint64_t>(max_batch, std::max<uint64_t>(1, present / 16)), total - pos);
+        const uint32_t start = reinsert ? (uint32_t)(num - 1 - pos) : (uint32_t)(first + pos);
+        gb::iota_kernel<<<(unsigned)((bsz + 255) / 256), 256, 0, stream>>>(b->d_ids, (uint32_t)bsz, start, reinsert ? -1 : 1);
+        h->launches++;
+        // candidates = search_for_neighbors(layer, prev_layers.search(e,1,1), e, max_search) (:819-820)
+        rc = enqueue_search(h, b->ws, b->d_ids, bsz, gb::kQueryById, ef, ef, b->d_cand_ids, b->d_cand_d, b->d_cand_cnt,
+                            nullptr, stream, false);
+        if (rc) return rc;
+        GB_CUDA(cudaMemsetAsync(b->d_counter, 0, 16, stream));
+        LinkLaunch L{h, {}, link_smem, 0, stream, false};
+        L.a.ids = b->d_ids;
+        L.a.n_batch = (uint32_t)bsz;
+        L.a.cand_ids = b->d_cand_ids;
+        L.a.cand_dists = b->d_cand_d;
+        L.a.cand_counts = b->d_cand_cnt;
+        L.a.cand_stride = ef;
+        L.a.rows = rows;
+        L.a.stride = b->stride;
+        L.a.node_width = b->cfg.num_neighbors;
+        L.a.max_neighbors = layer_m;
+        L.a.locks = b->d_locks;
+        L.a.stg_rows = plan.stg_rows;
+        L.a.work_counter = b->d_counter;
+        L.a.num_nodes = (uint32_t)num;
+        L.grid = (unsigned)std::min<uint64_t>(bsz, (uint64_t)h->num_sms * 8);
+        if ((rc = DistDispatch::call(d, L))) return rc;
+        pos += bsz;
+    }
+    // limit number of neighbors (:794-797)
+    GB_CUDA(cudaMemsetAsync(b->d_counter, 0, 16, stream));
+    LinkLaunch P{h, {}, plan.base_smem + 40 * 8 + 4 * 32 * 4 + 64, 0, stream, true};
+    P.a.rows = rows;
+    P.a.stride = b->stride;
+    P.a.node_width = b->cfg.num_neighbors;
+    P.a.max_neighbors = layer_m;
+    P.a.stg_rows = plan.stg_rows;
+    P.a.work_counter = b->d_counter;
+    P.a.num_nodes = (uint32_t)num;
+    P.grid = (unsigned)std::min<uint64_t>(num, (uint64_t)h->num_sms * 8);
+    if ((rc = DistDispatch::call(d, P))) return rc;
+    GB_CUDA(cudaStreamSynchronize(stream));
+    int herr[4] = {0, 0, 0, 0};
+    GB_CUDA(cudaMemcpy(herr, b->ws->d_error, sizeof(herr), cudaMemcpyDeviceToHost));
+    GB_CUDA(cudaMemset(b->ws->d_error, 0, sizeof(herr)));
+    return error_from_bits(herr[0]);
+}
+
+// index_elements_in_last_layer (:646-713)
+int builder_index_last_layer(Builder* b, uint64_t max_num_elements) {
+    Handle* h = b->h.get();
+    gb::DeviceIndex& d = h->dev;
+    const int cur = d.num_layers - 1;
+    const uint64_t total = b->cfg.expected_num_elements >= 0 ? (uint64_t)b->cfg.expected_num_elements : d.num_elements;
+    const uint64_t ideal =
+        gb::num_elements_in_layer(std::max<uint64_t>(total, d.num_elements), b->cfg.layer_multiplier, (uint64_t)cur);
+    const uint64_t have = d.layer_len[cur];
+    if (ideal <= have) return GRANNE_B200_OK;  // nothing to index in this layer
+    const uint64_t num = std::min<uint64_t>(max_num_elements, ideal);
+    uint32_t layer_m = b->cfg.num_neighbors;
+    if (ideal < total) layer_m = std::max<uint32_t>(1, layer_m / 2);  // half num_neighbors on upper layers
+    // the layer grows: fresh allocation (snapshots handed out by get_index keep the old one alive)
+    uint32_t* grown = nullptr;
+    GB_CUDA(cudaMalloc(&grown, std::max<size_t>((size_t)num * b->stride * 4, 16)));
+    std::shared_ptr<void> mem(grown, [](void* q) { cudaFree(q); });
+    cudaStream_t stream = b->ws->stream;
+    gb::fill_u32_kernel<<<h->num_sms * 4, 256, 0, stream>>>(grown, (unsigned long long)num * b->stride, gb::kUnusedId);
+    h->launches++;
+    if (have) GB_CUDA(cudaMemcpyAsync(grown, d.layer_rows[cur], (size_t)have * b->stride * 4, cudaMemcpyDeviceToDevice, stream));
+    b->layer_mem[cur] = mem;
+    d.layer_rows[cur] = grown;
+    d.layer_len[cur] = num;
+    h->layer_max_degree[cur] = b->cfg.num_neighbors;
+    finish_handle(h);
+    int rc = builder_index_elements(b, layer_m, b->cfg.max_search, have, num, false);
+    if (rc) return rc;
+    if (b->cfg.reinsert_elements) {
+        // use half max_search when reindexing (:698-699)
+        rc = builder_index_elements(b, layer_m, std::max<uint32_t>(1, b->cfg.max_search / 2), 0, num, true);
+        if (rc) return rc;
+    }
+    return GRANNE_B200_OK;
+}
+
+// build_partial (:374-402)
+int builder_build_partial(Builder* b, uint64_t num_elements) {
+    Handle* h = b->h.get();
+    gb::DeviceIndex& d = h->dev;
+    if (num_elements == 0) return GRANNE_B200_OK;
+    if (num_elements < h->index_len)
+        return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "Cannot index fewer elements than already in index.");
+    if (num_elements > d.num_elements)
+        return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "Cannot index more elements than exist.");
+    GB_CUDA(cudaSetDevice(h->device));
+    int rc;
+    if (d.num_layers > 0 && (rc = builder_index_last_layer(b, num_elements))) return rc;
+    while (h->index_len < num_elements) {
+        if (d.num_layers >= gb::kMaxLayers) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "too many layers");
+        // new layer = clone of the previous one (:392-398)
+        const int l = d.num_layers;
+        d.layer_rows[l] = l ? d.layer_rows[l - 1] : nullptr;
+        d.layer_len[l] = l ? d.layer_len[l - 1] : 0;
+        d.layer_width[l] = b->stride;
+        d.num_layers = l + 1;
+        b->layer_mem.push_back(l ? b->layer_mem[l - 1] : std::shared_ptr<void>());
+        h->layer_max_degree.push_back(b->cfg.num_neighbors);
+        finish_handle(h);
+        if ((rc = builder_index_last_layer(b, num_elements))) return rc;
+    }
+    return GRANNE_B200_OK;
+}
+
 }  // namespace
 
 // =================================================================================================================
@@ -600,7 +845,7 @@ void granne_b200_close(granne_b200_index* h) {
     h->pool.clear();
     for (auto& kv : h->stream_ws) ws_destroy(kv.second.get());
     h->stream_ws.clear();
-    for (void* p : h->allocations) cudaFree(p);
+    h->allocations.clear();
     delete h;
 }
 
@@ -776,6 +1021,182 @@ int granne_b200_decode_layer(const void* index_bytes, size_t index_len, uint64_t
     } catch (const std::exception& e) {
         return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, std::string("exception: ") + e.what());
     }
+}
+
+// ---- GranneBuilder ------------------------------------------------------------------------------------------------
+void granne_b200_build_config_default(granne_b200_build_config* cfg) {
+    if (!cfg) return;
+    cfg->layer_multiplier = 15.0f;
+    cfg->expected_num_elements = -1;
+    cfg->num_neighbors = 30;
+    cfg->max_search = 200;
+    cfg->reinsert_elements = 1;
+    cfg->show_progress = 0;
+}
+
+int granne_b200_builder_new(const granne_b200_build_config* cfg, int element_kind, const void* elements_bytes,
+                            size_t elements_len, const void* embeddings_bytes, size_t embeddings_len, int device,
+                            granne_b200_builder** out) {
+    try {
+        if (!out || !cfg) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "null argument");
+        *out = nullptr;
+        int rc = check_open_args(elements_bytes, element_kind, embeddings_bytes);
+        if (rc) return rc;
+        if (cfg->num_neighbors < 1 || cfg->num_neighbors > 31)
+            return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "num_neighbors must be in 1..31 for the GPU builder");
+        if (cfg->max_search < 1) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "max_search must be >= 1");
+        if (!(cfg->layer_multiplier > 1.0f))
+            return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "layer_multiplier must be > 1");
+        std::unique_ptr<granne_b200_builder> b(new granne_b200_builder());
+        b->cfg = *cfg;
+        b->stride = (cfg->num_neighbors + 7u) & ~7u;
+        b->h.reset(new Handle());
+        Handle* h = b->h.get();
+        rc = check_device(device, &h->num_sms, &h->smem_optin);
+        if (rc) return rc;
+        h->device = device;
+        GB_CUDA(cudaSetDevice(device));
+        rc = stage_elements(h, element_kind, static_cast<const uint8_t*>(elements_bytes), elements_len,
+                            static_cast<const uint8_t*>(embeddings_bytes), embeddings_len);
+        if (rc) return rc;
+        if (h->dev.num_elements >= 0xFFFFFFFFull)  // assert!(elements.len() < UNUSED) (:420)
+            return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "too many elements");
+        h->dev.num_layers = 0;
+        finish_handle(h);
+        if ((rc = ws_acquire(h, &b->ws))) return rc;
+        GB_CUDA(cudaMemset(b->ws->d_error, 0, 4 * sizeof(int)));
+        *out = b.release();
+        return GRANNE_B200_OK;
+    } catch (const std::exception& e) {
+        return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, std::string("exception: ") + e.what());
+    }
+}
+
+int granne_b200_builder_build(granne_b200_builder* b, uint64_t num_elements) {
+    if (!b) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "builder is null");
+    try {
+        return builder_build_partial(b, num_elements ? num_elements : b->h->dev.num_elements);
+    } catch (const std::exception& e) {
+        return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, std::string("exception: ") + e.what());
+    }
+}
+
+uint64_t granne_b200_builder_len(const granne_b200_builder* b) { return b ? b->h->index_len : 0; }
+uint64_t granne_b200_builder_num_layers(const granne_b200_builder* b) { return b ? (uint64_t)b->h->dev.num_layers : 0; }
+uint64_t granne_b200_builder_layer_len(const granne_b200_builder* b, uint64_t layer) {
+    if (!b || layer >= (uint64_t)b->h->dev.num_layers) return 0;
+    return b->h->dev.layer_len[layer];
+}
+
+int granne_b200_builder_write_index(granne_b200_builder* b, void* out, size_t cap, size_t* out_len) {
+    if (!b || !out_len) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "null argument");
+    try {
+        Handle* h = b->h.get();
+        GB_CUDA(cudaSetDevice(h->device));
+        std::vector<std::vector<uint32_t>> host(h->dev.num_layers);
+        std::vector<gb::LayerView> views;
+        for (int l = 0; l < h->dev.num_layers; ++l) {
+            const size_t n = (size_t)h->dev.layer_len[l] * b->stride;
+            host[l].resize(n);
+            if (n) GB_CUDA(cudaMemcpy(host[l].data(), h->dev.layer_rows[l], n * 4, cudaMemcpyDeviceToHost));
+            views.push_back({host[l].data(), h->dev.layer_len[l], b->stride});
+        }
+        std::vector<uint8_t> image;
+        std::string err;
+        if (!gb::encode_index(views, &image, &err)) return fail(GRANNE_B200_ERR_FORMAT, err);
+        *out_len = image.size();
+        if (!out) return GRANNE_B200_OK;
+        if (cap < image.size()) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "output buffer too small");
+        std::memcpy(out, image.data(), image.size());
+        return GRANNE_B200_OK;
+    } catch (const std::exception& e) {
+        return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, std::string("exception: ") + e.what());
+    }
+}
+
+int granne_b200_builder_get_index(granne_b200_builder* b, granne_b200_index** out) {
+    if (!b || !out) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "null argument");
+    try {
+        const Handle* src = b->h.get();
+        std::unique_ptr<Handle> h(new Handle());
+        h->device = src->device;
+        h->num_sms = src->num_sms;
+        h->smem_optin = src->smem_optin;
+        h->dev = src->dev;
+        h->allocations = src->allocations;  // shared ownership of the staged elements
+        for (const auto& m : b->layer_mem)
+            if (m) h->allocations.push_back(m);
+        h->device_bytes = src->device_bytes;
+        h->layer_max_degree = src->layer_max_degree;
+        finish_handle(h.get());
+        *out = h.release();
+        return GRANNE_B200_OK;
+    } catch (const std::exception& e) {
+        return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, std::string("exception: ") + e.what());
+    }
+}
+
+void granne_b200_builder_free(granne_b200_builder* b) {
+    if (!b) return;
+    cudaSetDevice(b->h->device);
+    cudaDeviceSynchronize();
+    cudaFree(b->d_ids);
+    cudaFree(b->d_cand_ids);
+    cudaFree(b->d_cand_d);
+    cudaFree(b->d_cand_cnt);
+    cudaFree(b->d_locks);
+    cudaFree(b->d_counter);
+    if (b->ws) {
+        ws_destroy(b->ws);
+        delete b->ws;
+    }
+    delete b;
+}
+
+int granne_b200_elements_from_raw(int element_kind, const float* raw, uint64_t n, uint32_t dim, int device, void* out,
+                                  size_t cap, size_t* out_len) {
+    if (!out_len) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "null argument");
+    if (element_kind != GRANNE_B200_ANGULAR && element_kind != GRANNE_B200_ANGULAR_INT)
+        return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "elements_from_raw builds angular or angular_int vectors");
+    if (dim == 0 || dim > 8192) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "dim must be in 1..8192");
+    const size_t esz = element_kind == GRANNE_B200_ANGULAR ? 4 : 1;
+    const size_t need = 8 + (size_t)n * dim * esz;
+    *out_len = need;
+    if (!out) return GRANNE_B200_OK;
+    if (cap < need) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "output buffer too small");
+    if (n && !raw) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "null argument");
+    int sms = 0;
+    size_t optin = 0;
+    int rc = check_device(device, &sms, &optin);
+    if (rc) return rc;
+    GB_CUDA(cudaSetDevice(device));
+    uint8_t* o = static_cast<uint8_t*>(out);
+    for (int b8 = 0; b8 < 8; ++b8) o[b8] = (uint8_t)((uint64_t)dim >> (8 * b8));
+    const uint64_t slab = std::max<uint64_t>(1, (256ull << 20) / ((size_t)dim * 4));
+    float* d_raw = nullptr;
+    void* d_out = nullptr;
+    const uint64_t rows_alloc = std::min<uint64_t>(slab, std::max<uint64_t>(n, 1));
+    GB_CUDA(cudaMalloc(&d_raw, rows_alloc * dim * 4));
+    cudaError_t e = cudaMalloc(&d_out, rows_alloc * dim * esz);
+    if (e != cudaSuccess) {
+        cudaFree(d_raw);
+        GB_CUDA(e);
+    }
+    for (uint64_t r0 = 0; r0 < n && rc == GRANNE_B200_OK; r0 += slab) {
+        const uint64_t nr = std::min(slab, n - r0);
+        e = cudaMemcpy(d_raw, raw + r0 * dim, (size_t)nr * dim * 4, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) {
+            gb::make_elements_kernel<<<(unsigned)std::min<uint64_t>(nr, (uint64_t)sms * 32), 32, (size_t)dim * 4>>>(
+                d_raw, nr, dim, element_kind, d_out);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess)
+            e = cudaMemcpy(o + 8 + (size_t)r0 * dim * esz, d_out, (size_t)nr * dim * esz, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = fail(GRANNE_B200_ERR_CUDA, cudaGetErrorString(e));
+    }
+    cudaFree(d_raw);
+    cudaFree(d_out);
+    return rc;
 }
 
 int granne_b200_merge_topk_device(int device, const uint32_t* d_part_ids, const float* d_part_dists,

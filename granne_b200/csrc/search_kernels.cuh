@@ -39,7 +39,7 @@ constexpr int kTileStride = 36;  // floats per tile row: 16-byte aligned rows, c
 constexpr int kTileBytes = 32 * kTileStride * 4 + 128;  // tile + 32 x u32 id scratch
 
 enum ElementKind : int { kAngularF32 = 0, kAngularI8 = 1, kSumEmbeddings = 2 };
-enum QueryFormat : int { kQueryRawF32 = 0, kQueryElement = 1 };
+enum QueryFormat : int { kQueryRawF32 = 0, kQueryElement = 1, kQueryById = 2 };  // ById: builder only (u32 ids)
 
 // per-query status bits (device side)
 constexpr int kStatusOverflow = 1;   // workspace too small for an exact answer -> slow path
@@ -964,12 +964,54 @@ __device__ __forceinline__ void search_layer_fast(const DeviceIndex& ix, WarpCtx
     *out_n = n;
 }
 
+// ElementContainer::get(id) written into the query slot c.qs (natural layout; i8: zero padded words + q_norm_i8).
+// Used by the builder (queries are elements of the container, src/index/mod.rs:817) and get_element.
+__device__ __forceinline__ void load_element_to_qs(const DeviceIndex& ix, WarpCtx& c, uint32_t id) {
+    const int lane = c.lane;
+    const uint32_t dim = ix.dim;
+    __syncwarp();
+    if (ix.kind == kAngularI8) {
+        int* qw = reinterpret_cast<int*>(c.qs);
+        const int* row = reinterpret_cast<const int*>(static_cast<const int8_t*>(ix.vectors) +
+                                                      (size_t)id * ix.row_stride);
+        const int words = ix.row_stride / 4;
+        int dy = 0;
+        for (int w = lane; w < words; w += 32) {
+            const int v = __ldg(row + w);
+            qw[w] = v;
+            dy = __dp4a(v, v, dy);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dy += __shfl_xor_sync(kFullMask, dy, o);
+        c.q_norm_i8 = dy;
+    } else if (ix.kind == kAngularF32) {
+        const float* row = static_cast<const float*>(ix.vectors) + (size_t)id * ix.row_stride;
+        const uint32_t V = ix.vec_group;
+        for (uint32_t e = lane; e < dim; e += 32) {
+            uint32_t o = e;
+            if (e < ix.full * 32) {
+                const uint32_t ch = e / 32, i = e % 32, g = ch / V, vv = ch % V;
+                o = g * 32 * V + i * V + vv;
+            }
+            c.qs[e] = __ldg(row + o);
+        }
+    } else {
+        DistSum::materialise(ix, c, id);
+        for (uint32_t e = lane; e < dim; e += 32) c.qs[e] = c.xs[e];
+    }
+    __syncwarp();
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // query construction (the `Elements::Element` the reference's callers build)
 // ------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void prepare_query(const DeviceIndex& ix, const SearchArgs& a, WarpCtx& c,
                                               unsigned long long qi) {
     const int dim = ix.dim, lane = c.lane;
+    if (a.query_format == kQueryById) {
+        load_element_to_qs(ix, c, static_cast<const uint32_t*>(a.queries)[qi]);
+        return;
+    }
     if (ix.kind == kAngularI8) {
         int* qw = reinterpret_cast<int*>(c.qs);
         int8_t* qb = reinterpret_cast<int8_t*>(c.qs);

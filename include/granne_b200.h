@@ -163,6 +163,50 @@ int granne_b200_inspect_index(const void* index_bytes, size_t index_len, uint64_
 int granne_b200_decode_layer(const void* index_bytes, size_t index_len, uint64_t layer, uint32_t* rows,
                              size_t rows_cap_u32);
 
+/* ---- GranneBuilder --------------------------------------------------------------------------
+ * GPU-side construction of the index: the reference's GranneBuilder (src/index/mod.rs:295-531, 645-960) with the
+ * insertions of a layer issued in batches (the reference issues them through rayon, :773-783).  Candidate search is
+ * the same kernel that serves granne_b200_search_batch; select_neighbors / connect_nodes / add_and_limit_neighbors run
+ * as device kernels with the reference's exact arithmetic.  As with the reference's default (multi-threaded) build the
+ * graph depends on the interleaving of concurrent insertions; quality is checked through recall, not bit parity. */
+
+/* BuildConfig (src/index/mod.rs:198-291); granne_b200_build_config_default() fills the reference defaults (:220-231). */
+typedef struct granne_b200_build_config {
+    float layer_multiplier;        /* 15.0 */
+    int64_t expected_num_elements; /* < 0 == None */
+    uint32_t num_neighbors;        /* 30; this implementation supports 1..31 */
+    uint32_t max_search;           /* 200 */
+    int32_t reinsert_elements;     /* 1 */
+    int32_t show_progress;         /* accepted for compatibility, ignored */
+} granne_b200_build_config;
+void granne_b200_build_config_default(granne_b200_build_config* cfg);
+
+typedef struct granne_b200_builder granne_b200_builder;
+
+/* GranneBuilder::new(config, elements) (:419-426).  Element buffers as in granne_b200_open. */
+int granne_b200_builder_new(const granne_b200_build_config* cfg, int element_kind, const void* elements_bytes,
+                            size_t elements_len, const void* embeddings_bytes, size_t embeddings_len, int device,
+                            granne_b200_builder** out);
+/* Builder::build_partial(num_elements) (:374-402); num_elements == 0 means Builder::build() (all elements, :366-368). */
+int granne_b200_builder_build(granne_b200_builder* b, uint64_t num_elements);
+uint64_t granne_b200_builder_len(const granne_b200_builder* b);        /* Index::len for the builder (:329-331) */
+uint64_t granne_b200_builder_num_layers(const granne_b200_builder* b); /* :334-336 */
+uint64_t granne_b200_builder_layer_len(const granne_b200_builder* b, uint64_t layer);
+/* Index::write_index (:358-361, src/index/io.rs:11-70): the granne index file image (compressed layers).  Call with
+ * out == NULL to query the size; the image is readable by granne itself and by granne_b200_open. */
+int granne_b200_builder_write_index(granne_b200_builder* b, void* out, size_t cap, size_t* out_len);
+/* GranneBuilder::get_index (:483-488): a searchable snapshot sharing the staged elements (no file round trip).
+ * Close it with granne_b200_close; it stays valid after further builder calls and after the builder is freed. */
+int granne_b200_builder_get_index(granne_b200_builder* b, granne_b200_index** out);
+void granne_b200_builder_free(granne_b200_builder* b);
+
+/* Element construction on the device: `angular::Vector::from(Vec<f32>)` per row — normalise (angular.rs:55-61,
+ * math.rs:124-150) or quantise to i8 (angular_int.rs:28-45) — written as an elements file image
+ * (FixedWidthSliceVector::write, src/slice_vector/mod.rs:460-466: u64 dim + rows).  kind: ANGULAR or ANGULAR_INT.
+ * Call with out == NULL to query the size. */
+int granne_b200_elements_from_raw(int element_kind, const float* raw, uint64_t n, uint32_t dim, int device, void* out,
+                                  size_t cap, size_t* out_len);
+
 /* Number of kernels this library launched on behalf of `h` since it was opened (bench.py's gpu_launches). */
 uint64_t granne_b200_launch_count(const granne_b200_index* h);
 

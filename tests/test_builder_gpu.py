@@ -1,0 +1,121 @@
+"""GPU GranneBuilder: built like the reference's own build tests check it
+(src/index/tests.rs:41-132: self-recall > 0.95; :305-335 layer sizes; :337-451 write/load round trip), plus: an index
+written by the GPU builder is a valid granne file (the CPU oracle loads it) and searching it on the GPU is
+bit-identical to the oracle searching the same file."""
+import numpy as np
+import pytest
+
+import granne_b200
+from helpers.data import clustered_vectors, random_vectors
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _lib():
+    from granne_b200 import build
+
+    build.build()
+    granne_b200.load_library()
+
+
+def test_elements_from_raw_matches_vector_from(oracle):
+    raw = random_vectors(300, 100, seed=1)
+    raw[7] = 0.0  # the zero vector stays zero (norm == 0, math.rs:141)
+    eb = granne_b200.elements_from_raw("angular", raw).tobytes()
+    assert eb == oracle.Elements.angular(raw).to_bytes()
+    ib = granne_b200.elements_from_raw("angular_int", raw).tobytes()
+    assert ib == oracle.Elements.angular_int(raw).to_bytes()
+    for dim in [3, 28, 32, 33, 128]:
+        r = random_vectors(50, dim, seed=dim)
+        assert granne_b200.elements_from_raw("angular", r).tobytes() == oracle.Elements.angular(r).to_bytes()
+
+
+def _self_recall(index, rows, max_search):
+    ids, dists, counts = index.search_batch(rows, max_search, 1, already_element=True)
+    return float((ids[:, 0] == np.arange(rows.shape[0])).mean())
+
+
+@pytest.mark.parametrize("kind,n,dim", [("angular", 1500, 28), ("angular_int", 500, 32), ("angular", 3000, 128)])
+def test_build_and_search_like_the_reference(oracle, kind, n, dim):
+    # build_and_search_float / build_and_search_int8 (src/index/tests.rs:41-62,114-132): M=20, max_search=20,
+    # then every element must find itself with max_search = 10
+    raw = random_vectors(n, dim, seed=n)
+    eb = granne_b200.elements_from_raw(kind, raw).tobytes()
+    b = granne_b200.GranneBuilder(kind, eb, num_neighbors=20, max_search=20)
+    b.build()
+    assert len(b) == n
+    expect_layers = []
+    l = 0
+    while not expect_layers or expect_layers[-1] < n:  # compute_num_elements_in_layer (:634-643)
+        expect_layers.append(oracle.num_elements_in_layer(n, 15.0, l))
+        l += 1
+    assert [b.layer_len(i) for i in range(b.num_layers())] == expect_layers
+    index = b.get_index()
+    el = oracle.Elements.from_bytes(kind, eb)
+    rows = el.rows()
+    assert _self_recall(index, rows, 10) > 0.95
+    # degrees respect num_neighbors (and num_neighbors / 2 on upper layers, :665-668)
+    for layer in range(index.num_layers()):
+        limit = 20 if layer == index.num_layers() - 1 else 10
+        for i in range(0, index.layer_len(layer), 37):
+            nb = index.get_neighbors(i, layer)
+            assert len(nb) <= limit and len(set(nb)) == len(nb) and i not in nb
+    # the written index is a valid granne file: the oracle loads it, and both sides search it identically
+    image = b.index_bytes().tobytes()
+    g = oracle.Granne.from_bytes(image, el)
+    assert [g.layer_len(i) for i in range(g.num_layers())] == expect_layers
+    for layer in range(g.num_layers()):
+        for i in range(0, g.layer_len(layer), 53):
+            assert g.get_neighbors(i, layer) == sorted(index.get_neighbors(i, layer))
+    p = granne_b200.Granne.from_bytes(image, kind, eb)
+    q = random_vectors(100, dim, seed=5)
+    ref = g.search_batch(q, 50, 10, with_stats=True)
+    got = p.search_batch(q, 50, 10, with_stats=True)
+    assert np.array_equal(ref[0], got[0]) and np.array_equal(ref[1].view(np.uint32), got[1].view(np.uint32))
+    assert np.array_equal(ref[3][:, :3], got[3][:, :3])
+    p.close()
+    index.close()
+    b.close()
+
+
+def test_incremental_build_and_snapshots(oracle):
+    # incremental_build_* (src/index/tests.rs:134-242): build_partial in steps; earlier snapshots stay valid
+    raw = random_vectors(1200, 25, seed=9)
+    eb = granne_b200.elements_from_raw("angular", raw).tobytes()
+    b = granne_b200.GranneBuilder("angular", eb, num_neighbors=20, max_search=20, expected_num_elements=1200)
+    b.build(0 + 300)
+    snap = b.get_index()
+    assert len(b) == 300 and len(snap) == 300
+    b.build(900)
+    b.build()
+    assert len(b) == 1200 and len(snap) == 300
+    rows = oracle.Elements.from_bytes("angular", eb).rows()
+    assert _self_recall(snap, rows[:300], 40) > 0.95
+    full = b.get_index()
+    assert _self_recall(full, rows, 40) > 0.95
+    with pytest.raises(granne_b200.GranneError):
+        b.build(100)  # "Cannot index fewer elements than already in index." (:379-382)
+    snap.close()
+    full.close()
+    b.close()
+
+
+def test_recall_against_brute_force():
+    import torch
+
+    n, dim = 50_000, 64
+    raw = clustered_vectors(n, dim, seed=3)
+    eb = granne_b200.elements_from_raw("angular", raw).tobytes()
+    b = granne_b200.GranneBuilder("angular", eb, num_neighbors=30, max_search=200)
+    b.build()
+    index = b.get_index()
+    q = clustered_vectors(512, dim, seed=4)
+    ids, d, c = index.search_batch(q, 200, 10)
+    rows = torch.from_numpy(np.frombuffer(eb, dtype=np.float32, offset=8).reshape(n, dim).copy()).cuda()
+    qn = torch.nn.functional.normalize(torch.from_numpy(q).cuda(), dim=1)
+    gt = torch.topk(qn @ rows.T, 10, dim=1).indices.cpu().numpy()
+    recall = np.mean([len(set(gt[i]) & set(ids[i].tolist())) / 10 for i in range(512)])
+    assert recall > 0.95, recall
+    index.close()
+    b.close()
