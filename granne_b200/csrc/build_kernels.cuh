@@ -172,6 +172,8 @@ __device__ __forceinline__ void setup_ctx(const DeviceIndex& ix, WarpCtx& c, Lin
     sp += kTileBytes;
     c.bar = smem_u32(sp);
     c.phase = 0;
+    c.pol_stream = make_policy_evict_first();
+    c.pol_keep = make_policy_evict_last();
     sp += 16;
     const uint32_t qbytes = (ix.kind == kAngularI8) ? ix.row_stride : ((ix.dim + 3u) & ~3u) * 4u;
     c.qs = reinterpret_cast<float*>(sp);

@@ -315,7 +315,7 @@ LaunchPlan make_plan(const Handle* h, uint32_t max_search) {
     p.stg_rows = 0;
     if (p.staged) {
         const uint32_t row_bytes = d.full * 128u;
-        p.stg_rows = std::min<uint32_t>(16, std::max<uint32_t>(4, (8192u / row_bytes) & ~3u));
+        p.stg_rows = std::min<uint32_t>(16, std::max<uint32_t>(4, (4096u / row_bytes) & ~3u));
         base = ((base + 127) & ~size_t(127)) + (size_t)p.stg_rows * row_bytes;
     }
     p.base_smem = base;

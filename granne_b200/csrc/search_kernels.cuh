@@ -150,6 +150,8 @@ struct WarpCtx {
     uint32_t stg_rows;   // rows that fit in the staging tile (<= 16)
     uint32_t bar;        // shared-space address of the mbarrier the bulk copies signal
     uint32_t phase;      // its current phase parity
+    unsigned long long pol_stream;  // L2 policy evict_first: candidate rows are read once per query
+    unsigned long long pol_keep;    // L2 policy evict_last: the per-warp visited tables are re-read all the time
     int lane;
     int status;
     int q_norm_i8;     // ANGULAR_INT: dy = sum q^2
@@ -179,10 +181,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     } while (!ok);
 }
 // global -> shared, `bytes` multiple of 16, both addresses 16-byte aligned; completion is counted on `bar`.
-__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar,
+                                              unsigned long long policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+        "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ unsigned long long make_policy_evict_first() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ unsigned long long make_policy_evict_last() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
 }
 
 // Strictly ordered sum of the 32 lane partials of ONE value (used where only a single candidate is live):
@@ -250,7 +264,8 @@ struct DistF32 {
                 if (c.lane == 0) mbar_arrive_expect_tx(c.bar, (uint32_t)nb * copy_bytes);
                 if (c.lane < nb)
                     bulk_copy_g2s(smem_u32(c.stg) + c.lane * copy_bytes,
-                                  static_cast<const char*>(ix.vectors) + (size_t)id * stride_bytes, copy_bytes, c.bar);
+                                  static_cast<const char*>(ix.vectors) + (size_t)id * stride_bytes, copy_bytes, c.bar,
+                                  c.pol_stream);
                 mbar_wait(c.bar, c.phase);
                 c.phase ^= 1u;
                 const unsigned char* mine = c.stg + c.lane * (V * 4);
@@ -448,21 +463,31 @@ __device__ __forceinline__ bool vis_insert(uint32_t* tab, uint32_t slots, uint32
 // has a single writer warp and conflicts between lanes of that warp are resolved in registers with match.any.
 // Returns true in lanes whose id was newly inserted.  Sets *overflow when a home bucket is full (-> slow path).
 // ------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint4 ldcg_u4(const uint32_t* p) {
+__device__ __forceinline__ uint4 ldcg_u4(const uint32_t* p, unsigned long long policy) {
     uint4 v;
-    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    asm volatile("ld.global.cg.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p), "l"(policy));
     return v;
 }
+__device__ __forceinline__ void stcg_u32(uint32_t* p, uint32_t v, unsigned long long policy) {
+    asm volatile("st.global.cg.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void stcg_u4(uint4* p, uint4 v, unsigned long long policy) {
+    asm volatile("st.global.cg.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+                 "r"(v.w), "l"(policy)
+                 : "memory");
+}
 __device__ __forceinline__ bool vis_bucket_insert(uint32_t* tab, uint32_t nbuckets, uint32_t id, bool valid,
-                                                  bool* overflow) {
+                                                  bool* overflow, unsigned long long policy) {
     uint32_t b = __umulhi(id * 0x9E3779B1u, nbuckets);
     bool pending = valid, is_new = false;
     for (int probe = 0;; ++probe) {
         uint32_t* bucket = tab + (size_t)b * 8u;
         uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
         if (pending) {
-            lo = ldcg_u4(bucket);
-            hi = ldcg_u4(bucket + 4);
+            lo = ldcg_u4(bucket, policy);
+            hi = ldcg_u4(bucket + 4, policy);
         }
         const bool found = (lo.x == id) | (lo.y == id) | (lo.z == id) | (lo.w == id) | (hi.x == id) |
                            (hi.y == id) | (hi.z == id) | (hi.w == id);
@@ -485,7 +510,7 @@ __device__ __forceinline__ bool vis_bucket_insert(uint32_t* tab, uint32_t nbucke
             if (ins) {
                 const uint32_t slot = used + __popc(same_b & lanemask_lt());
                 if (slot < 8u) {
-                    __stcg(bucket + slot, id);
+                    stcg_u32(bucket + slot, id, policy);
                     is_new = true;
                     pending = false;
                 }
@@ -753,7 +778,7 @@ __device__ __forceinline__ void search_layer_fast(const DeviceIndex& ix, WarpCtx
     {
         uint4* v4 = reinterpret_cast<uint4*>(c.visited);
         const uint4 e = make_uint4(kUnusedId, kUnusedId, kUnusedId, kUnusedId);
-        for (uint32_t i = lane; i < nbuckets * 2; i += 32) __stcg(v4 + i, e);
+        for (uint32_t i = lane; i < nbuckets * 2; i += 32) stcg_u4(v4 + i, e, c.pol_keep);
     }
     for (uint32_t i = lane; i < P; i += 32) Ld[i] = kDMask;  // sentinel: larger than any distance, never flagged
     __syncwarp();
@@ -769,7 +794,7 @@ __device__ __forceinline__ void search_layer_fast(const DeviceIndex& ix, WarpCtx
             return;
         }
         bool ovf = false;
-        vis_bucket_insert(c.visited, nbuckets, entrypoint, lane == 0, &ovf);
+        vis_bucket_insert(c.visited, nbuckets, entrypoint, lane == 0, &ovf, c.pol_keep);
         if (lane == 0) {
             Ld[0] = __float_as_uint(d0);
             Li[0] = entrypoint;
@@ -777,6 +802,7 @@ __device__ __forceinline__ void search_layer_fast(const DeviceIndex& ix, WarpCtx
         __syncwarp();
     }
     uint32_t n = 1, n_exp = 0, cursor = 0, pos_thr = 0, thr_bits = 0;
+    uint32_t spec_id = kUnusedId, spec_nb = kUnusedId;
 
     while (true) {
         // ---- pq.pop(): first unexpanded entry at or after the cursor; also find the runner-up ----
@@ -796,14 +822,18 @@ __device__ __forceinline__ void search_layer_fast(const DeviceIndex& ix, WarpCtx
         const uint32_t xd = Ld[px];  // unflagged
         const uint32_t xid = Li[px];
         if (n_exp >= ef && xd > thr_bits) break;
-        // warm L2 with the adjacency row of the most likely next expansion (the runner-up in the same 32-entry row)
+        // Speculation: the runner-up of this pop (next unexpanded entry of the same 32-entry row) is the most likely
+        // next expansion.  Its adjacency row is loaded into a register now (one lane = one neighbour, width <= 32)
+        // so that the load latency overlaps this whole expansion; a wrong guess only costs the load.
+        uint32_t cur_nb = kUnusedId;
+        const bool have_cur = (spec_id == xid) && (width <= 32u);
+        if (have_cur) cur_nb = spec_nb;
+        spec_id = kUnusedId;
         {
             const unsigned rest = sel_mask & (sel_mask - 1);
-            if (rest) {
-                const uint32_t yid = Li[base_sel + __ffs(rest) - 1];
-                if ((uint32_t)lane * 32u < width * 4u)
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(rows + (size_t)yid * width) +
-                                                                  lane * 32));
+            if (rest && width <= 32u) {
+                spec_id = Li[base_sel + __ffs(rest) - 1];
+                spec_nb = ((uint32_t)lane < width) ? __ldg(rows + (size_t)spec_id * width + lane) : kUnusedId;
             }
         }
 
@@ -842,13 +872,13 @@ __device__ __forceinline__ void search_layer_fast(const DeviceIndex& ix, WarpCtx
         // ---- neighbours ----
         const uint32_t* row = rows + (size_t)xid * width;
         for (uint32_t w0 = 0; w0 < width; w0 += 32) {
-            const uint32_t nb = (w0 + lane < width) ? __ldg(row + w0 + lane) : kUnusedId;
+            const uint32_t nb = have_cur ? cur_nb : ((w0 + lane < width) ? __ldg(row + w0 + lane) : kUnusedId);
             const bool valid = nb != kUnusedId;
             const unsigned vm = __ballot_sync(kFullMask, valid);
             if (vm == 0) break;
             c.n_nbr += __popc(vm);
             bool ovf = false;
-            const bool is_new = vis_bucket_insert(c.visited, nbuckets, nb, valid, &ovf);
+            const bool is_new = vis_bucket_insert(c.visited, nbuckets, nb, valid, &ovf, c.pol_keep);
             const unsigned nm = __ballot_sync(kFullMask, is_new);
             const int k = __popc(nm);
             vis_count += k;
@@ -869,6 +899,11 @@ __device__ __forceinline__ void search_layer_fast(const DeviceIndex& ix, WarpCtx
                 return;
             }
             const uint32_t my_d = __float_as_uint(d);
+            if (spec_id != kUnusedId && spec_nb != kUnusedId) {
+                // the speculative row has had a whole distance phase to arrive: warm L2 with its visited buckets
+                const uint32_t pb = __umulhi(spec_nb * 0x9E3779B1u, nbuckets);
+                asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(c.visited + (size_t)pb * 8u));
+            }
             // !res.is_full() || distance < res.peek().0   (:1029)
             bool pass = (lane < k) && (n_exp < ef || my_d < thr_bits);
             // a key strictly farther than the last entry of a full list has >= ef strictly closer entries before
@@ -1086,7 +1121,7 @@ __device__ __forceinline__ void prepare_query(const DeviceIndex& ix, const Searc
 // R == 0: generic list (64-bit keys, any capacity, shared or global memory) — the slow pass and very large max_search.
 // R  > 0: fast list with capacity 32*R for the bottom layer (upper layers always use R = 1).
 template <class Dist, int R>
-__global__ void __launch_bounds__(32, R > 0 ? 16 : 1) search_kernel(const DeviceIndex ix, const SearchArgs a) {
+__global__ void __launch_bounds__(32, R > 0 ? 20 : 1) search_kernel(const DeviceIndex ix, const SearchArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WarpCtx c;
     c.lane = threadIdx.x;
@@ -1098,6 +1133,8 @@ __global__ void __launch_bounds__(32, R > 0 ? 16 : 1) search_kernel(const Device
     sp += kTileBytes;
     c.bar = smem_u32(sp);
     c.phase = 0;
+    c.pol_stream = make_policy_evict_first();
+    c.pol_keep = make_policy_evict_last();
     sp += 16;
     const uint32_t qbytes = (ix.kind == kAngularI8) ? ix.row_stride : ((ix.dim + 3u) & ~3u) * 4u;
     c.qs = reinterpret_cast<float*>(sp);
