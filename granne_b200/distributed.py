@@ -1,0 +1,156 @@
+"""Multi-GPU search: one process per GPU, torch.distributed (NCCL over NVLink/NVSwitch) for the plumbing.
+
+Queries are independent (Granne::search takes &self, src/index/mod.rs:140-150), so the path shards without any
+data-path collective; the only exchange is the collection of the small result tiles.
+
+Mode 1 — ReplicatedGranne: the staged index is replicated on every GPU, each rank searches its own slice of the query
+batch, the [nq_local, k] result tiles are all-gathered.  Results are bit-identical to a single-GPU search of the same
+queries.
+
+Mode 2 — PartitionedGranne: the element set is split into contiguous id ranges with one independent granne index per
+range (the reference's own notion of sharding, src/elements/embeddings/parsing.rs:63-100); every rank searches ALL
+queries on its shard, the per-shard tiles are all-gathered and merged per query by (distance, global id) — the tuple
+order of into_sorted_vec (src/index/mod.rs:1036).  The merge runs on the GPU (granne_b200_merge_topk_device).
+
+The collective calls work on whatever backend the process group uses; on CPU tensors (gloo, used by the host-logic
+tests) the merge uses merge_topk_host below, which is the numpy statement of the same k-way merge.
+"""
+import numpy as np
+
+
+def shard_bounds(n, world, rank):
+    """Contiguous, balanced [begin, end) of `n` items for `rank` (the first n % world ranks get one extra)."""
+    base, extra = divmod(n, world)
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+def merge_topk_host(part_ids, part_dists, part_base, k):
+    """k-way merge of per-shard tiles on the host.  part_ids: [P, nq, k] uint32 (0xFFFFFFFF padded), part_dists:
+    [P, nq, k] float32, part_base: P global id offsets.  Returns (int64 [nq, k] padded with -1, float32 padded +inf)."""
+    part_ids = np.asarray(part_ids)
+    part_dists = np.asarray(part_dists)
+    P, nq, kk = part_ids.shape
+    out_ids = np.full((nq, k), -1, dtype=np.int64)
+    out_d = np.full((nq, k), np.inf, dtype=np.float32)
+    for q in range(nq):
+        cand = []
+        for p in range(P):
+            for j in range(kk):
+                lid = int(part_ids[p, q, j])
+                if lid == 0xFFFFFFFF:
+                    break
+                cand.append((part_dists[p, q, j], int(part_base[p]) + lid))
+        cand.sort(key=lambda t: (t[0], t[1]))
+        for r, (d, gid) in enumerate(cand[:k]):
+            out_ids[q, r] = gid
+            out_d[q, r] = d
+    return out_ids, out_d
+
+
+class ReplicatedGranne:
+    """Index replicated per rank, query batch sharded, results all-gathered.
+
+    local_search(queries, max_search, k) -> (ids int32/uint32 [nq_local, k], dists float32 [nq_local, k]) as torch
+    tensors on the collective's device; by default the rank's granne_b200.Granne.search_batch_device."""
+
+    def __init__(self, index=None, group=None, local_search=None):
+        import torch.distributed as dist
+
+        self.dist = dist
+        self.group = group
+        self.index = index
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self._local = local_search or self._search_device
+
+    def _search_device(self, q, max_search, k):
+        ids, dists, _ = self.index.search_batch_device(q, max_search, k)
+        return ids, dists
+
+    def my_slice(self, nq_global):
+        return shard_bounds(nq_global, self.world, self.rank)
+
+    def search_local_shard(self, local_queries, max_search=200, k=10, out=None):
+        """Every rank passes ITS slice (equal sizes); returns the gathered [world * nq_local, k] tiles in rank order."""
+        import torch
+
+        ids, dists = self._local(local_queries, max_search, k)
+        if self.world == 1:
+            return ids, dists
+        nq = ids.shape[0]
+        if out is None:
+            out = (torch.empty((self.world * nq, k), dtype=ids.dtype, device=ids.device),
+                   torch.empty((self.world * nq, k), dtype=dists.dtype, device=dists.device))
+        self.dist.all_gather_into_tensor(out[0], ids.contiguous(), group=self.group)
+        self.dist.all_gather_into_tensor(out[1], dists.contiguous(), group=self.group)
+        return out
+
+    def search_batch(self, queries, max_search=200, k=10):
+        """`queries` is the same global batch on every rank; each rank searches its slice and all ranks receive the
+        full result in query order (uneven slices are padded for the collective and trimmed afterwards)."""
+        import torch
+
+        nq = queries.shape[0]
+        b, e = self.my_slice(nq)
+        per = -(-nq // self.world)
+        local = queries[b:e]
+        if e - b < per:  # pad with a repeat of the last query so every rank contributes `per` rows
+            pad = queries[e - 1:e] if e > b else queries[:1]
+            local = torch.cat([local] + [pad] * (per - (e - b)), dim=0)
+        ids, dists = self.search_local_shard(local, max_search, k)
+        if self.world == 1:
+            return ids[:nq], dists[:nq]
+        keep = []
+        for r in range(self.world):
+            rb, re = shard_bounds(nq, self.world, r)
+            keep.append(torch.arange(r * per, r * per + (re - rb), device=ids.device))
+        keep = torch.cat(keep)
+        return ids[keep], dists[keep]
+
+
+class PartitionedGranne:
+    """One independent index per contiguous id range (one per rank); all queries searched on every shard; per-shard
+    tiles all-gathered and merged by (distance, global id)."""
+
+    def __init__(self, index=None, shard_base=0, group=None, local_search=None, device_index=0):
+        import torch
+        import torch.distributed as dist
+
+        self.dist = dist
+        self.group = group
+        self.index = index
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self._local = local_search or self._search_device
+        self.device_index = device_index
+        bases = [None] * self.world
+        if self.world > 1:
+            dist.all_gather_object(bases, int(shard_base), group=group)
+        else:
+            bases = [int(shard_base)]
+        self.bases = bases
+        self._torch = torch
+
+    def _search_device(self, q, max_search, k):
+        ids, dists, _ = self.index.search_batch_device(q, max_search, k)
+        return ids, dists
+
+    def search_batch(self, queries, max_search=200, k=10):
+        torch = self._torch
+        ids, dists = self._local(queries, max_search, k)
+        nq = ids.shape[0]
+        if self.world > 1:
+            flat_ids = torch.empty((self.world * nq, k), dtype=ids.dtype, device=ids.device)
+            flat_d = torch.empty((self.world * nq, k), dtype=dists.dtype, device=dists.device)
+            self.dist.all_gather_into_tensor(flat_ids, ids.contiguous(), group=self.group)
+            self.dist.all_gather_into_tensor(flat_d, dists.contiguous(), group=self.group)
+            all_ids, all_d = flat_ids.view(self.world, nq, k), flat_d.view(self.world, nq, k)
+        else:
+            all_ids, all_d = ids[None], dists[None]
+        if all_ids.is_cuda:
+            from .api import merge_topk_device
+
+            return merge_topk_device(self.device_index, all_ids, all_d, self.bases)
+        gi, gd = merge_topk_host(all_ids.numpy().view(np.uint32), all_d.numpy(), self.bases, k)
+        return torch.from_numpy(gi), torch.from_numpy(gd)

@@ -357,3 +357,21 @@ def test_merge_topk_matches_a_cpu_merge(oracle):
         assert np.array_equal(out_d[qi].cpu().numpy(), np.array([e[0] for e in exp], dtype=np.float32))
     for _, _, p in shards:
         p.close()
+
+
+def test_multi_gpu_modes_under_torchrun():
+    """Replicated / range-partitioned parity over NCCL (tests/multi_gpu_check.py) when the box has >= 2 GPUs."""
+    import os
+    import subprocess
+    import sys
+
+    import torch
+
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(min(n, 8)),
+           "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "multi_gpu_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "multi-gpu check ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
