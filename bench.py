@@ -265,12 +265,12 @@ def main():
     q_host = clustered(a.nq * pool, a.dim, seed=4321 + rank, n_centers=n_centers)
     q_dev = torch.from_numpy(q_host).to(dev)
     streams = [torch.cuda.Stream(device=dev) for _ in range(max(1, a.streams))]
-    outs = [(torch.empty((a.nq, a.k), dtype=torch.int32, device=dev), torch.empty((a.nq, a.k), dtype=torch.float32,
-             device=dev), torch.empty((a.nq,), dtype=torch.int32, device=dev)) for _ in streams]
+    # per stream: one int32 buffer [2, nq, k] = ids | distance bits (a single all-gather collects both), + counts
+    bufs = [torch.empty((2, a.nq, a.k), dtype=torch.int32, device=dev) for _ in streams]
+    outs = [(b[0], b[1].view(torch.float32), torch.empty((a.nq,), dtype=torch.int32, device=dev)) for b in bufs]
     gathered = None
     if world > 1:
-        gathered = [(torch.empty((world * a.nq, a.k), dtype=torch.int32, device=dev),
-                     torch.empty((world * a.nq, a.k), dtype=torch.float32, device=dev)) for _ in streams]
+        gathered = [torch.empty((world * 2 * a.nq, a.k), dtype=torch.int32, device=dev) for _ in streams]
 
     def device_step(s):
         st = streams[s % len(streams)]
@@ -278,10 +278,8 @@ def main():
         qb = q_dev[(s % pool) * a.nq:(s % pool + 1) * a.nq]
         with torch.cuda.stream(st):
             index.search_batch_device(qb, a.max_search, a.k, out=o, stream=st.cuda_stream)
-            if world > 1:
-                g = gathered[s % len(streams)]
-                dist.all_gather_into_tensor(g[0], o[0])
-                dist.all_gather_into_tensor(g[1], o[1])
+            if world > 1:  # collect every rank's result tile (NCCL all-gather over NVLink)
+                dist.all_gather_into_tensor(gathered[s % len(streams)], bufs[s % len(streams)].view(2 * a.nq, a.k))
 
     def sync_all():
         for st in streams:
@@ -330,6 +328,7 @@ def main():
         sampler.start()
     launches0 = index.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.nvtx.range_push("timed")
     e0.record(torch.cuda.current_stream(dev))
     for st in streams:
         st.wait_stream(torch.cuda.current_stream(dev))
@@ -339,6 +338,7 @@ def main():
         torch.cuda.current_stream(dev).wait_stream(st)
     e1.record(torch.cuda.current_stream(dev))
     sync_all()
+    torch.cuda.nvtx.range_pop()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
