@@ -551,6 +551,7 @@ int enqueue_search(Handle* h, Workspace* w, const void* d_queries, size_t nq, in
     a.out_stats = d_stats;
     a.query_status = w->d_status;
     a.work_counter = w->d_counters;
+    a.overflow_seen = w->d_counters + 2;
     a.error_flag = w->d_error;
     a.slow_list = w->d_slow_list;
     a.slow_visited = w->d_slow_vis;

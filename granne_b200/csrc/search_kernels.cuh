@@ -81,6 +81,7 @@ struct SearchArgs {
     unsigned long long* out_stats;  // nq x 4 or null
     int* query_status;              // nq ints (0 = done ok)
     unsigned int* work_counter;     // persistent scheduling
+    unsigned int* overflow_seen;    // set by the fast pass when any query needs the slow pass
     int* error_flag;                // sticky device error word (OR of status bits that are final)
     // slow path only: global workspaces (one per slow CTA)
     unsigned long long* slow_list;
@@ -1170,6 +1171,7 @@ __global__ void __launch_bounds__(32, R > 0 ? 20 : 1) search_kernel(const Device
         }
     }
     Dist dist;
+    if (a.slow_pass && *reinterpret_cast<volatile unsigned int*>(a.overflow_seen) == 0u) return;  // nothing flagged
 
     while (true) {
         unsigned int qi0 = 0;
@@ -1270,7 +1272,10 @@ __global__ void __launch_bounds__(32, R > 0 ? 20 : 1) search_kernel(const Device
             // leave the outputs to the slow path (or report capacity exhaustion if this IS the slow path)
             if (c.lane == 0) {
                 a.query_status[qi] = a.slow_pass ? (kStatusOverflow | 4) : kStatusOverflow;
-                if (a.slow_pass) atomicOr(a.error_flag, kStatusOverflow);
+                if (a.slow_pass)
+                    atomicOr(a.error_flag, kStatusOverflow);
+                else
+                    atomicExch(a.overflow_seen, 1u);
             }
             if (!a.slow_pass) continue;
             found = 0;
