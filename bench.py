@@ -49,6 +49,8 @@ def parse_args():
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--num-neighbors", type=int, default=30)
     ap.add_argument("--streams", type=int, default=4)
+    ap.add_argument("--kind", default="angular", choices=["angular", "angular_int"],
+                    help="element type (angular_int = BASELINE config 3 style i8/dp4a path)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target duration of the cpu_baseline sample")
     return ap.parse_args()
 
@@ -70,12 +72,14 @@ def clustered(n, dim, seed, n_centers, sub_dim=16, spread=0.3, basis_seed=7):
 
 
 def workload_config(a, impl):
-    return {"workload": "%dx%d angular f32 HNSW (M=%d, build max_search=200), search max_search=%d k=%d, "
-                        "%d queries/step/GPU" % (a.n, a.dim, a.num_neighbors, a.max_search, a.k, a.nq),
-            "baseline_config": "BASELINE.json configs[1]", "n": a.n, "dim": a.dim, "max_search": a.max_search,
+    et = "f32" if a.kind == "angular" else "i8"
+    return {"workload": "%dx%d angular %s HNSW (M=%d, build max_search=200), search max_search=%d k=%d, "
+                        "%d queries/step/GPU" % (a.n, a.dim, et, a.num_neighbors, a.max_search, a.k, a.nq),
+            "baseline_config": "BASELINE.json configs[1]" if a.kind == "angular" else "BASELINE.json configs[2] family",
+            "n": a.n, "dim": a.dim, "max_search": a.max_search,
             "k": a.k, "queries_per_step_per_gpu": a.nq, "index": "replicated, queries sharded" if a.gpus > 1
             else "single GPU", "l2": "inputs larger than L2 (%.0f MB vectors + adjacency; query batches rotate)"
-            % (a.n * a.dim * 4 / 1e6), "streams": a.streams, "impl": impl}
+            % (a.n * a.dim * (4 if a.kind == "angular" else 1) / 1e6), "streams": a.streams, "impl": impl}
 
 
 class ClockSampler:
@@ -139,7 +143,7 @@ def cpu_baseline(index_bytes, elements_bytes, queries, a, seconds):
     from oracle import granne_oracle as go
 
     threads = os.cpu_count() or 1
-    el = go.Elements.from_bytes("angular", elements_bytes)
+    el = go.Elements.from_bytes(a.kind, elements_bytes)
     g = go.Granne.from_bytes(index_bytes, el)          # compressed adjacency decoded per expansion (faithful)
     gf = g.to_fixed()                                  # pre-decoded adjacency (the stronger CPU variant)
     probe = queries[:max(threads * 2, 64)]
@@ -170,7 +174,7 @@ def run_reference(a):
     threads = os.cpu_count() or 1
     n_centers = max(8, int(4096 * (a.n / 1e6) ** 0.5))
     raw = clustered(a.n, a.dim, seed=1234, n_centers=n_centers)
-    el = go.Elements.angular(raw)
+    el = go.Elements.angular(raw) if a.kind == "angular" else go.Elements.angular_int(raw)
     del raw
     t0 = time.time()
     g = go.GranneBuilder(el, num_neighbors=a.num_neighbors, max_search=200).build(threads=threads).to_fixed()
@@ -191,7 +195,7 @@ def run_reference(a):
     qps = a.steps * per_step / dt
     line = {"metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "impl": "reference", "config": workload_config(a, "reference"),
+            "dtype": "f32" if a.kind == "angular" else "i8", "data": "synthetic", "impl": "reference", "config": workload_config(a, "reference"),
             "cpu_baseline": {"value": qps, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": "%d queries per step (bounded), pre-decoded adjacency, %d threads; index built "
                                        "by the oracle's threaded builder in %.0f s" % (per_step, threads, build_s)},
@@ -232,12 +236,12 @@ def main():
     n_centers = max(8, int(4096 * (a.n / 1e6) ** 0.5))
     t0 = time.time()
     raw = clustered(a.n, a.dim, seed=1234, n_centers=n_centers)
-    elements_bytes = granne_b200.elements_from_raw("angular", raw, device=local)
+    elements_bytes = granne_b200.elements_from_raw(a.kind, raw, device=local)
     del raw
     t_data = time.time() - t0
     t0 = time.time()
     if rank == 0:
-        builder = granne_b200.GranneBuilder("angular", elements_bytes, num_neighbors=a.num_neighbors, max_search=200,
+        builder = granne_b200.GranneBuilder(a.kind, elements_bytes, num_neighbors=a.num_neighbors, max_search=200,
                                             device=local)
         builder.build()
         index_bytes = builder.index_bytes()
@@ -256,7 +260,7 @@ def main():
         del buf
         if rank == 0:
             builder.close()
-        index = granne_b200.Granne.from_bytes(index_bytes, "angular", elements_bytes, device=local)
+        index = granne_b200.Granne.from_bytes(index_bytes, a.kind, elements_bytes, device=local)
     elif rank == 0:
         builder.close()
 
@@ -293,13 +297,22 @@ def main():
     index.stream_status()
     st_np = stats.cpu().numpy()
     n_dist, n_expand, n_nbr = st_np[:, 0].mean(), st_np[:, 1].mean(), st_np[:, 2].mean()
-    bytes_per_query = n_dist * a.dim * 4 + n_nbr * 4 + a.dim * 4  # vectors + adjacency ids + query
+    esz = 4 if a.kind == "angular" else 1
+    bytes_per_query = n_dist * a.dim * esz + n_nbr * 4 + a.dim * esz  # vectors + adjacency + query
     nsamp = min(256, a.nq)
-    rows = torch.from_numpy(np.frombuffer(elements_bytes, dtype=np.float32, offset=8).reshape(a.n, a.dim))
-    qn = torch.nn.functional.normalize(q_dev[:nsamp], dim=1)
+    if a.kind == "angular":
+        rows = torch.from_numpy(np.frombuffer(elements_bytes, dtype=np.float32, offset=8).reshape(a.n, a.dim))
+        qn = torch.nn.functional.normalize(q_dev[:nsamp], dim=1)
+    else:  # ground truth under the same i8 angular distance: cosine of the quantised vectors
+        rows = torch.from_numpy(np.frombuffer(elements_bytes, dtype=np.int8, offset=8).reshape(a.n, a.dim))
+        qq = q_dev[:nsamp]
+        qq = torch.trunc(qq * 127.0 / qq.abs().amax(dim=1, keepdim=True))
+        qn = torch.nn.functional.normalize(qq, dim=1)
     best = None
     for s0 in range(0, a.n, 1 << 18):  # exact brute force in slabs (off the hot path)
         blk = rows[s0:s0 + (1 << 18)].to(dev)
+        if a.kind != "angular":
+            blk = torch.nn.functional.normalize(blk.float(), dim=1)
         sc = qn @ blk.T
         v, i = torch.topk(sc, a.k, dim=1)
         i = i + s0
@@ -417,7 +430,7 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": workload_config(a, "ours"),
+        "dtype": "f32" if a.kind == "angular" else "i8", "data": "synthetic", "config": workload_config(a, "ours"),
         "recall_at_10": recall,
         "e2e": {"value": e2e_qps, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "host_threads": nthreads, "api": "granne_b200.Granne.search_batch (granne_b200_search_batch)"},
@@ -425,7 +438,7 @@ def main():
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src,
-                     "kernel": "search_kernel<DistF32<4>,7> (1 launch per step)",
+                     "kernel": "search_kernel<%s,7> (1 launch per step)" % ("DistF32<4>" if a.kind == "angular" else "DistI8"),
                      "algorithmic_bytes_per_query": bytes_per_query,
                      "algorithmic_bytes_per_launch": bytes_per_query * a.nq,
                      "n_dist_per_query": n_dist, "n_expand_per_query": n_expand,

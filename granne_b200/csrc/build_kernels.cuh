@@ -29,6 +29,7 @@ struct BuildArgs {
     uint32_t max_neighbors;     // config.num_neighbors of THIS layer (halved on upper layers, :665-668)
     int* locks;                 // one spin lock per node
     uint32_t stg_rows;
+    uint32_t stg_row_bytes;
     unsigned int* work_counter;
     uint32_t num_nodes;         // prune pass: nodes in the layer
 };
@@ -164,7 +165,7 @@ __device__ __forceinline__ void connect_nodes(const DeviceIndex& ix, WarpCtx& c,
 
 template <class Dist>
 __device__ __forceinline__ void setup_ctx(const DeviceIndex& ix, WarpCtx& c, LinkScratch& s, unsigned char* smem_raw,
-                                          uint32_t stg_rows, uint32_t cand_cap) {
+                                          uint32_t stg_rows, uint32_t stg_row_bytes, uint32_t cand_cap) {
     c.lane = threadIdx.x;
     unsigned char* sp = smem_raw;
     c.tile = reinterpret_cast<float*>(sp);
@@ -185,7 +186,7 @@ __device__ __forceinline__ void setup_ctx(const DeviceIndex& ix, WarpCtx& c, Lin
     if (Dist::kStaged) {
         sp = smem_raw + (((size_t)(sp - smem_raw) + 127u) & ~(size_t)127u);
         c.stg = sp;
-        sp += (size_t)stg_rows * ix.full * 128u;
+        sp += (size_t)stg_rows * stg_row_bytes;
         if (c.lane == 0) mbar_init(c.bar, 1);
         __syncwarp();
     }
@@ -214,7 +215,7 @@ __global__ void __launch_bounds__(32) build_link_kernel(const DeviceIndex ix, co
     WarpCtx c;
     LinkScratch s;
     const uint32_t cand_cap = a.cand_stride > 40 ? a.cand_stride : 40;
-    setup_ctx<Dist>(ix, c, s, smem_raw, a.stg_rows, cand_cap);
+    setup_ctx<Dist>(ix, c, s, smem_raw, a.stg_rows, a.stg_row_bytes, cand_cap);
     Dist dist;
     const int lane = c.lane;
     while (true) {
@@ -286,7 +287,7 @@ __global__ void __launch_bounds__(32) build_prune_kernel(const DeviceIndex ix, c
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WarpCtx c;
     LinkScratch s;
-    setup_ctx<Dist>(ix, c, s, smem_raw, a.stg_rows, 40);
+    setup_ctx<Dist>(ix, c, s, smem_raw, a.stg_rows, a.stg_row_bytes, 40);
     Dist dist;
     while (true) {
         unsigned int w0 = 0;

@@ -284,13 +284,15 @@ struct LaunchPlan {
     uint32_t list_cap, vis_slots, vis_upper;
     int rows;           // fast list rows R (capacity 32*R), 0 = generic list
     uint32_t stg_rows;  // candidate rows per bulk-copy batch (staged distance engines only)
+    uint32_t stg_row_bytes;
     size_t base_smem;   // tile + mbarrier + query (+ embeddings scratch) + staging
     size_t smem;        // fast pass total
     bool staged;
 };
 
 bool is_staged_kind(const gb::DeviceIndex& d) {
-    // DistF32<FULL> with FULL > 0 (see dispatch_search)
+    // DistI8, and DistF32<FULL> with FULL > 0 (see dispatch_search)
+    if (d.kind == gb::kAngularI8) return true;
     return d.kind == gb::kAngularF32 && d.full > 0 && !(d.vec_group == 1 && d.full > 4) &&
            (d.full <= 4 || d.full == 6 || d.full == 8);
 }
@@ -313,8 +315,10 @@ LaunchPlan make_plan(const Handle* h, uint32_t max_search) {
     size_t base = gb::kTileBytes + 16 + ((qbytes + 15u) & ~15u) * (d.kind == gb::kSumEmbeddings ? 2 : 1);
     p.staged = is_staged_kind(d);
     p.stg_rows = 0;
+    p.stg_row_bytes = 0;
     if (p.staged) {
-        const uint32_t row_bytes = d.full * 128u;
+        const uint32_t row_bytes = d.kind == gb::kAngularI8 ? d.row_stride : d.full * 128u;
+        p.stg_row_bytes = row_bytes;
         p.stg_rows = std::min<uint32_t>(16, std::max<uint32_t>(4, (4096u / row_bytes) & ~3u));
         base = ((base + 127) & ~size_t(127)) + (size_t)p.stg_rows * row_bytes;
     }
@@ -559,6 +563,7 @@ int enqueue_search(Handle* h, Workspace* w, const void* d_queries, size_t nq, in
     a.slow_vis_slots = h->slow_vis_slots;
     a.slow_pass = 0;
     a.stg_rows = plan.stg_rows;
+    a.stg_row_bytes = plan.stg_row_bytes;
     a.vis_global = nullptr;
     return dispatch_search(h, w, a, plan, stream);
 }
@@ -707,6 +712,7 @@ int builder_index_elements(Builder* b, uint32_t layer_m, uint32_t ef, uint64_t a
         L.a.max_neighbors = layer_m;
         L.a.locks = b->d_locks;
         L.a.stg_rows = plan.stg_rows;
+        L.a.stg_row_bytes = plan.stg_row_bytes;
         L.a.work_counter = b->d_counter;
         L.a.num_nodes = (uint32_t)num;
         L.grid = (unsigned)std::min<uint64_t>(bsz, (uint64_t)h->num_sms * 8);
@@ -721,6 +727,7 @@ int builder_index_elements(Builder* b, uint32_t layer_m, uint32_t ef, uint64_t a
     P.a.node_width = b->cfg.num_neighbors;
     P.a.max_neighbors = layer_m;
     P.a.stg_rows = plan.stg_rows;
+    P.a.stg_row_bytes = plan.stg_row_bytes;
     P.a.work_counter = b->d_counter;
     P.a.num_nodes = (uint32_t)num;
     P.grid = (unsigned)std::min<uint64_t>(num, (uint64_t)h->num_sms * 8);

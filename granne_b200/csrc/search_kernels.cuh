@@ -74,7 +74,8 @@ struct SearchArgs {
     uint32_t vis_slots;       // visited slots for the bottom layer
     uint32_t vis_slots_upper; // visited slots for the max_search = 1 descents
     uint32_t* vis_global;     // fast pass: one table of vis_slots u32 per CTA in global memory (L2 resident)
-    uint32_t stg_rows;        // fast pass: candidate rows per bulk-copy batch (0 = this element kind loads directly)
+    uint32_t stg_rows;        // candidate rows per bulk-copy batch (0 = this element kind loads directly)
+    uint32_t stg_row_bytes;   // bytes of one staged row (f32: 128*FULL, i8: row_stride)
     uint32_t* out_ids;
     float* out_dists;
     uint32_t* out_counts;
@@ -156,7 +157,7 @@ struct WarpCtx {
     int lane;
     int status;
     int q_norm_i8;     // ANGULAR_INT: dy = sum q^2
-    uint32_t n_dist, n_expand, n_nbr, n_ins;
+    uint32_t n_dist, n_expand, n_nbr, n_ins, n_spec;
 };
 
 // ---- mbarrier + 1-D bulk copy (TMA, UBLKCP) helpers ----------------------------------------------------------------
@@ -339,33 +340,42 @@ struct DistF32Generic {
 };
 
 // ANGULAR_INT i8: exact i32 r, dx via dp4a (src/math.rs:59-89), then 1 - r/(sqrt(dx)*sqrt(dy)) in IEEE f32
-// (src/elements/angular_int.rs:47-59).  Rows and the query are zero-padded to row_stride bytes.
+// (src/elements/angular_int.rs:47-59).  Rows and the query are zero-padded to row_stride bytes (multiple of 16).
+// Candidate rows are bulk-copied into the staging tile like the f32 rows; lane w then handles 32-bit word w of a row
+// and the exact integer sums are reduced with REDUX (__reduce_add_sync) — integer addition is order independent.
 struct DistI8 {
-    static constexpr bool kStaged = false;
+    static constexpr bool kStaged = true;
     __device__ __forceinline__ void load_query(const DeviceIndex&, const WarpCtx&) {}
     __device__ __forceinline__ float dists(const DeviceIndex& ix, WarpCtx& c, uint32_t my_id, int k) {
-        const int8_t* base = static_cast<const int8_t*>(ix.vectors);
-        const size_t stride = ix.row_stride;
-        const int words = ix.row_stride / 4;
+        const uint32_t stride = ix.row_stride;
+        const int words = stride / 4;
         const int* qw = reinterpret_cast<const int*>(c.qs);
         int my_r = 0, my_dx = 0;
-        for (int j = 0; j < k; ++j) {
-            const uint32_t id = __shfl_sync(kFullMask, my_id, j);
-            const int* row = reinterpret_cast<const int*>(base + (size_t)id * stride);
-            int r = 0, dx = 0;
-            for (int w = c.lane; w < words; w += 32) {
-                const int a = ldg_row_i32(row + w);
-                r = __dp4a(a, qw[w], r);
-                dx = __dp4a(a, a, dx);
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                r += __shfl_xor_sync(kFullMask, r, o);
-                dx += __shfl_xor_sync(kFullMask, dx, o);
-            }
-            if (c.lane == j) {
-                my_r = r;
-                my_dx = dx;
+        const int rb = (int)c.stg_rows;
+        for (int j0 = 0; j0 < k; j0 += rb) {
+            const int nb = (k - j0) < rb ? (k - j0) : rb;
+            const uint32_t id = __shfl_sync(kFullMask, my_id, (j0 + c.lane) & 31);
+            __syncwarp();  // everyone is done reading the previous batch
+            if (c.lane == 0) mbar_arrive_expect_tx(c.bar, (uint32_t)nb * stride);
+            if (c.lane < nb)
+                bulk_copy_g2s(smem_u32(c.stg) + c.lane * stride,
+                              static_cast<const char*>(ix.vectors) + (size_t)id * stride, stride, c.bar, c.pol_stream);
+            mbar_wait(c.bar, c.phase);
+            c.phase ^= 1u;
+            for (int b = 0; b < nb; ++b) {
+                const int* row = reinterpret_cast<const int*>(c.stg + (size_t)b * stride);
+                int r = 0, dx = 0;
+                for (int w = c.lane; w < words; w += 32) {
+                    const int a = row[w];
+                    r = __dp4a(a, qw[w], r);
+                    dx = __dp4a(a, a, dx);
+                }
+                r = __reduce_add_sync(kFullMask, r);
+                dx = __reduce_add_sync(kFullMask, dx);
+                if (c.lane == j0 + b) {
+                    my_r = r;
+                    my_dx = dx;
+                }
             }
         }
         float d = 0.0f;
@@ -376,6 +386,7 @@ struct DistI8 {
             const float dd = __fsub_rn(1.0f, qv);
             d = (0.0f <= dd) ? dd : 0.0f;
         }
+        __syncwarp();
         return d;
     }
 };
@@ -828,7 +839,10 @@ __device__ __forceinline__ void search_layer_fast(const DeviceIndex& ix, WarpCtx
         // so that the load latency overlaps this whole expansion; a wrong guess only costs the load.
         uint32_t cur_nb = kUnusedId;
         const bool have_cur = (spec_id == xid) && (width <= 32u);
-        if (have_cur) cur_nb = spec_nb;
+        if (have_cur) {
+            cur_nb = spec_nb;
+            c.n_spec += 1;
+        }
         spec_id = kUnusedId;
         {
             const unsigned rest = sel_mask & (sel_mask - 1);
@@ -933,16 +947,25 @@ __device__ __forceinline__ void search_layer_fast(const DeviceIndex& ix, WarpCtx
                 iv[t] = j < n ? Li[j] : 0u;
                 sh[t] = 0;
             }
-            uint32_t rank_n = 0;
+            uint32_t rank_n = 0, sh_base = 0;
             for (unsigned t = pm; t; t &= t - 1) {
                 const int j = __ffs(t) - 1;
                 const uint32_t rj = __shfl_sync(kFullMask, rank_l, j);
                 const uint32_t dj = __shfl_sync(kFullMask, my_d, j);
                 const uint32_t ij = __shfl_sync(kFullMask, my_id, j);
                 rank_n += (dj < my_d || (dj == my_d && ij < my_id)) ? 1u : 0u;
+                // keys ranked before my first position shift all my entries; a key ranked inside my R positions
+                // (rare) shifts only the entries at or after it
+                const uint32_t rel = rj - (uint32_t)(R * lane);  // wraps to a huge value when rj < R*lane
+                if (rj <= (uint32_t)(R * lane)) {
+                    sh_base += 1;
+                } else if (rel < (uint32_t)R) {
 #pragma unroll
-                for (int tt = 0; tt < R; ++tt) sh[tt] += (rj <= (uint32_t)(R * lane + tt)) ? 1u : 0u;
+                    for (int tt = 0; tt < R; ++tt) sh[tt] += (rel <= (uint32_t)tt) ? 1u : 0u;
+                }
             }
+#pragma unroll
+            for (int tt = 0; tt < R; ++tt) sh[tt] += sh_base;
             const uint32_t new_pos = rank_l + rank_n;
             const uint32_t total = n + m;
             uint32_t drop_flagged = 0;
@@ -1147,7 +1170,7 @@ __global__ void __launch_bounds__(32, R > 0 ? 20 : 1) search_kernel(const Device
     if (Dist::kStaged) {
         sp = smem_raw + (((size_t)(sp - smem_raw) + 127u) & ~(size_t)127u);
         c.stg = sp;
-        sp += (size_t)a.stg_rows * ix.full * 128u;
+        sp += (size_t)a.stg_rows * a.stg_row_bytes;
         if (c.lane == 0) mbar_init(c.bar, 1);
         __syncwarp();
     }
@@ -1181,7 +1204,7 @@ __global__ void __launch_bounds__(32, R > 0 ? 20 : 1) search_kernel(const Device
         if (a.slow_pass && a.query_status[qi] != kStatusOverflow) continue;  // only flagged queries
 
         c.status = 0;
-        c.n_dist = c.n_expand = c.n_nbr = c.n_ins = 0;
+        c.n_dist = c.n_expand = c.n_nbr = c.n_ins = c.n_spec = 0;
         c.q_norm_i8 = 0;
         prepare_query(ix, a, c, qi);
         dist.load_query(ix, c);
@@ -1294,7 +1317,8 @@ __global__ void __launch_bounds__(32, R > 0 ? 20 : 1) search_kernel(const Device
                 a.out_stats[qi * 4 + 0] = c.n_dist;
                 a.out_stats[qi * 4 + 1] = c.n_expand;
                 a.out_stats[qi * 4 + 2] = c.n_nbr;
-                a.out_stats[qi * 4 + 3] = (a.slow_pass ? 1ull : 0ull) | ((unsigned long long)c.n_ins << 8);
+                a.out_stats[qi * 4 + 3] = (a.slow_pass ? 1ull : 0ull) | ((unsigned long long)(c.n_ins & 0xFFFFFFu) << 8) |
+                                          ((unsigned long long)c.n_spec << 32);
             }
             if (!(c.status & kStatusOverflow)) a.query_status[qi] = 0;
         }
