@@ -272,9 +272,11 @@ def main():
     # per stream: one int32 buffer [2, nq, k] = ids | distance bits (a single all-gather collects both), + counts
     bufs = [torch.empty((2, a.nq, a.k), dtype=torch.int32, device=dev) for _ in streams]
     outs = [(b[0], b[1].view(torch.float32), torch.empty((a.nq,), dtype=torch.int32, device=dev)) for b in bufs]
-    gathered = None
+    gathered, groups = None, None
     if world > 1:
         gathered = [torch.empty((world * 2 * a.nq, a.k), dtype=torch.int32, device=dev) for _ in streams]
+        # one communicator per stream: collectives of different in-flight steps do not serialise behind each other
+        groups = [dist.new_group(backend="nccl") for _ in streams]
 
     def device_step(s):
         st = streams[s % len(streams)]
@@ -283,7 +285,8 @@ def main():
         with torch.cuda.stream(st):
             index.search_batch_device(qb, a.max_search, a.k, out=o, stream=st.cuda_stream)
             if world > 1:  # collect every rank's result tile (NCCL all-gather over NVLink)
-                dist.all_gather_into_tensor(gathered[s % len(streams)], bufs[s % len(streams)].view(2 * a.nq, a.k))
+                dist.all_gather_into_tensor(gathered[s % len(streams)], bufs[s % len(streams)].view(2 * a.nq, a.k),
+                                            group=groups[s % len(streams)])
 
     def sync_all():
         for st in streams:
@@ -420,7 +423,9 @@ def main():
     tp = os.path.join(ROOT, "profiles", "dram_traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            tj = json.load(open(tp))
+            if (tj.get("kind"), tj.get("n"), tj.get("dim"), tj.get("queries_per_launch")) == (a.kind, a.n, a.dim, a.nq):
+                traffic = tj.get("dram_bytes_per_launch")
         except Exception:
             traffic = None
     cpu = None

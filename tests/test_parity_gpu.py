@@ -71,6 +71,23 @@ def test_c1_parity_over_max_search_and_k(c1, ef, k):
     assert (got[2] == min(ef, k)).all()
 
 
+@pytest.mark.parametrize("ef", [600, 976, 977, 1500])
+def test_large_max_search_uses_wider_lists(c1, ef):
+    # 32*R list capacities up to R=31 (max_search <= 976), beyond that the generic 64-bit list is the fast pass
+    el, g, p = c1
+    q = random_vectors(24, 32, seed=ef)
+    assert_parity(*run_both(g, p, q, ef, 20), what="ef=%d" % ef)
+
+
+def test_rows_wider_than_a_warp(oracle):
+    # num_neighbors > 32: adjacency rows span two 32-id chunks (the speculative single-register row is bypassed)
+    el, g, ib, eb, _ = build_fixture(oracle, "angular", 2500, 24, seed=8, num_neighbors=45, max_search=60)
+    assert max(len(g.get_neighbors(i)) for i in range(0, 2500, 7)) > 32
+    p = open_product(ib, "angular", eb)
+    assert_parity(*run_both(g, p, random_vectors(200, 24, seed=9), 60, 10), what="M=45")
+    p.close()
+
+
 def test_c1_index_trait_and_get_element(c1, oracle):
     el, g, p = c1
     assert len(p) == len(g) == 10_000
