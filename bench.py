@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--num-neighbors", type=int, default=30)
     ap.add_argument("--streams", type=int, default=4)
+    ap.add_argument("--graphs", type=int, default=1, help="replay each step from a CUDA graph (0 = eager launches)")
     ap.add_argument("--kind", default="angular", choices=["angular", "angular_int"],
                     help="element type (angular_int = BASELINE config 3 style i8/dp4a path)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target duration of the cpu_baseline sample")
@@ -278,15 +279,37 @@ def main():
         # one communicator per stream: collectives of different in-flight steps do not serialise behind each other
         groups = [dist.new_group(backend="nccl") for _ in streams]
 
+    qin = [torch.empty((a.nq, a.dim), dtype=torch.float32, device=dev) for _ in streams]
+    graphs = [None] * len(streams)
+
+    def step_body(slot):
+        index.search_batch_device(qin[slot], a.max_search, a.k, out=outs[slot], stream=streams[slot].cuda_stream)
+        if world > 1:  # collect every rank's result tile (NCCL all-gather over NVLink)
+            dist.all_gather_into_tensor(gathered[slot], bufs[slot].view(2 * a.nq, a.k), group=groups[slot])
+
     def device_step(s):
-        st = streams[s % len(streams)]
-        o = outs[s % len(streams)]
-        qb = q_dev[(s % pool) * a.nq:(s % pool + 1) * a.nq]
+        slot = s % len(streams)
+        st = streams[slot]
         with torch.cuda.stream(st):
-            index.search_batch_device(qb, a.max_search, a.k, out=o, stream=st.cuda_stream)
-            if world > 1:  # collect every rank's result tile (NCCL all-gather over NVLink)
-                dist.all_gather_into_tensor(gathered[s % len(streams)], bufs[s % len(streams)].view(2 * a.nq, a.k),
-                                            group=groups[s % len(streams)])
+            qin[slot].copy_(q_dev[(s % pool) * a.nq:(s % pool + 1) * a.nq], non_blocking=True)
+            if graphs[slot] is not None:
+                graphs[slot].replay()
+            else:
+                step_body(slot)
+
+    def capture_graphs():
+        """One CUDA graph per stream slot: search kernels (+ the all-gather) replayed with a single launch."""
+        for slot, st in enumerate(streams):
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=st):
+                    step_body(slot)
+                graphs[slot] = g
+            except Exception as e:  # capture unsupported (e.g. NCCL build): fall back to eager launches
+                graphs[slot] = None
+                if rank == 0:
+                    print("cuda graph capture failed, running eagerly: %r" % (e,), file=sys.stderr)
+                break
 
     def sync_all():
         for st in streams:
@@ -333,9 +356,15 @@ def main():
     del rows
 
     # ---- device-resident timed region ------------------------------------------------------------------------------------
-    for s in range(a.warmup):
+    for s in range(max(a.warmup, len(streams))):
         device_step(s)
     sync_all()
+    if a.graphs:
+        capture_graphs()
+        sync_all()
+        for s in range(len(streams)):
+            device_step(s)
+        sync_all()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
@@ -348,8 +377,10 @@ def main():
     e0.record(torch.cuda.current_stream(dev))
     for st in streams:
         st.wait_stream(torch.cuda.current_stream(dev))
+    t_issue = time.perf_counter()
     for s in range(a.steps):
         device_step(a.warmup + s)
+    issue_ms = (time.perf_counter() - t_issue) * 1e3
     for st in streams:
         torch.cuda.current_stream(dev).wait_stream(st)
     e1.record(torch.cuda.current_stream(dev))
@@ -451,6 +482,7 @@ def main():
                      "solo_launch_gbs": bytes_per_query * a.nq / (solo_ms / 1e3) / 1e9},
         "cpu_baseline": cpu,
         "setup_s": {"data+elements": t_data, "gpu_index_build": t_build},
+        "host_issue_ms_per_step": issue_ms / a.steps, "cuda_graphs": bool(graphs[0] is not None),
     }
     print(json.dumps(line), flush=True)
     if world > 1:
