@@ -49,7 +49,10 @@ def parse_args():
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--num-neighbors", type=int, default=30)
     ap.add_argument("--streams", type=int, default=4)
-    ap.add_argument("--graphs", type=int, default=1, help="replay each step from a CUDA graph (0 = eager launches)")
+    ap.add_argument("--graphs", type=int, default=0, help="replay each step from a CUDA graph (0 = eager launches)")
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: p2p = kernels store result tiles into every peer's buffer (fused epilogue over "
+                         "NVLink peer memory); nccl = one all-gather per step")
     ap.add_argument("--kind", default="angular", choices=["angular", "angular_int"],
                     help="element type (angular_int = BASELINE config 3 style i8/dp4a path)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target duration of the cpu_baseline sample")
@@ -273,8 +276,21 @@ def main():
     # per stream: one int32 buffer [2, nq, k] = ids | distance bits (a single all-gather collects both), + counts
     bufs = [torch.empty((2, a.nq, a.k), dtype=torch.int32, device=dev) for _ in streams]
     outs = [(b[0], b[1].view(torch.float32), torch.empty((a.nq,), dtype=torch.int32, device=dev)) for b in bufs]
-    gathered, groups = None, None
-    if world > 1:
+    gathered, groups, fused = None, None, None
+    if world > 1 and a.gather == "p2p":
+        try:
+            from granne_b200.distributed import FusedGather
+
+            fused = FusedGather(a.nq, a.k, slots=len(streams))
+        except Exception as e:  # symmetric memory unavailable: use the NCCL all-gather
+            fused = None
+            if rank == 0:
+                print("fused peer gather unavailable (%r): falling back to NCCL all-gather" % (e,), file=sys.stderr)
+        ok = torch.tensor([1 if fused is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            fused = None
+    if world > 1 and fused is None:
         gathered = [torch.empty((world * 2 * a.nq, a.k), dtype=torch.int32, device=dev) for _ in streams]
         # one communicator per stream: collectives of different in-flight steps do not serialise behind each other
         groups = [dist.new_group(backend="nccl") for _ in streams]
@@ -282,7 +298,14 @@ def main():
     qin = [torch.empty((a.nq, a.dim), dtype=torch.float32, device=dev) for _ in streams]
     graphs = [None] * len(streams)
 
+    seq = [0]
+
     def step_body(slot):
+        if fused is not None:  # result tiles go straight into every peer's gathered buffer
+            seq[0] += 1
+            index.search_batch_device_gather(qin[slot], fused.spec(slot, seq[0]), a.max_search, a.k,
+                                             stream=streams[slot].cuda_stream)
+            return
         index.search_batch_device(qin[slot], a.max_search, a.k, out=outs[slot], stream=streams[slot].cuda_stream)
         if world > 1:  # collect every rank's result tile (NCCL all-gather over NVLink)
             dist.all_gather_into_tensor(gathered[slot], bufs[slot].view(2 * a.nq, a.k), group=groups[slot])
@@ -359,7 +382,7 @@ def main():
     for s in range(max(a.warmup, len(streams))):
         device_step(s)
     sync_all()
-    if a.graphs:
+    if a.graphs and fused is None:
         capture_graphs()
         sync_all()
         for s in range(len(streams)):
@@ -483,6 +506,8 @@ def main():
         "cpu_baseline": cpu,
         "setup_s": {"data+elements": t_data, "gpu_index_build": t_build},
         "host_issue_ms_per_step": issue_ms / a.steps, "cuda_graphs": bool(graphs[0] is not None),
+        "multi_gpu_gather": None if world == 1 else ("p2p peer stores fused into the search kernels" if fused is not None
+                                                     else "nccl all_gather"),
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -6,7 +6,7 @@ constructor arguments, same method names and defaults.  All computation happens 
 if the library is missing or no sm_100 device is present the calls fail loudly — there is no CPU fallback.
 """
 from .api import (ANGULAR, ANGULAR_INT, EMBEDDINGS, QUERY_ELEMENT, QUERY_RAW_F32, BuildConfig, Granne,  # noqa: F401
-                  GranneBuilder, GranneError, elements_from_raw,
+                  GranneBuilder, GranneError, PeerGather, elements_from_raw,
                   decode_layer, inspect_index, library_path, load_library, merge_topk_device)
 
 __all__ = ["Granne", "GranneBuilder", "BuildConfig", "elements_from_raw", "GranneError", "ANGULAR", "ANGULAR_INT", "EMBEDDINGS", "QUERY_RAW_F32", "QUERY_ELEMENT",

@@ -54,6 +54,7 @@ def load_library():
         "granne_b200_get_element": (i32, [vp, u64, vp]),
         "granne_b200_search_batch": (i32, [vp, vp, sz, i32, u32, u32, vp, vp, vp, vp]),
         "granne_b200_search_batch_device": (i32, [vp, vp, sz, i32, u32, u32, vp, vp, vp, vp, vp]),
+        "granne_b200_search_batch_device_gather": (i32, [vp, vp, sz, i32, u32, u32, vp, vp, vp, vp]),
         "granne_b200_stream_status": (i32, [vp]),
         "granne_b200_merge_topk_device": (i32, [i32, vp, vp, vp, sz, sz, u32, vp, vp, vp]),
         "granne_b200_inspect_index": (i32, [vp, sz, vp, vp, vp, vp, sz]),
@@ -239,6 +240,19 @@ class Granne:
             C.c_void_p(stats.data_ptr()) if stats is not None else None, C.c_void_p(s)))
         return ids, dists, counts
 
+    def search_batch_device_gather(self, queries, gather, max_search=DEFAULT_MAX_SEARCH,
+                                   num_elements=DEFAULT_NUM_ELEMENTS, already_element=False, counts=None, stream=None):
+        """Like search_batch_device, but the result rows are stored by the kernels straight into every peer's
+        gathered buffer described by `gather` (a PeerGather)."""
+        import torch
+
+        q = queries
+        fmt = QUERY_ELEMENT if already_element or q.dtype == torch.int8 else QUERY_RAW_F32
+        s = stream if stream is not None else torch.cuda.current_stream(q.device).cuda_stream
+        _check(load_library().granne_b200_search_batch_device_gather(
+            self._h, C.c_void_p(q.data_ptr()), q.shape[0], fmt, int(max_search), int(num_elements), C.byref(gather),
+            C.c_void_p(counts.data_ptr()) if counts is not None else None, None, C.c_void_p(s)))
+
     def stream_status(self):
         _check(load_library().granne_b200_stream_status(self._h))
 
@@ -247,6 +261,13 @@ class Granne:
 
     def device_bytes(self):
         return int(load_library().granne_b200_device_bytes(self._h))
+
+
+class PeerGather(C.Structure):
+    """granne_b200_peer_gather: peer-mapped result buffers for the fused multi-GPU gather."""
+    _fields_ = [("n_peers", C.c_uint32), ("my_rank", C.c_uint32), ("row_offset", C.c_uint64), ("seq", C.c_uint32),
+                ("reserved", C.c_uint32), ("ids", C.c_void_p * 8), ("dists", C.c_void_p * 8),
+                ("flags", C.c_void_p * 8)]
 
 
 class BuildConfig(C.Structure):

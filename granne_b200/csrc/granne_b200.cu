@@ -531,7 +531,7 @@ int validate_search(const Handle* h, const void* q, size_t nq, int fmt, uint32_t
 // Enqueues one batch on `stream` with device pointers.  Needs a workspace for status words / slow path.
 int enqueue_search(Handle* h, Workspace* w, const void* d_queries, size_t nq, int fmt, uint32_t max_search,
                    uint32_t k, uint32_t* d_ids, float* d_dists, uint32_t* d_counts, unsigned long long* d_stats,
-                   cudaStream_t stream, bool reset_error) {
+                   cudaStream_t stream, bool reset_error, const granne_b200_peer_gather* pg = nullptr) {
     const LaunchPlan plan = make_plan(h, max_search);
     if (plan.smem == 0 || max_search + 64 > h->slow_list_cap)
         return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "max_search exceeds the supported maximum (about 27000)");
@@ -562,6 +562,19 @@ int enqueue_search(Handle* h, Workspace* w, const void* d_queries, size_t nq, in
     a.slow_list_cap = h->slow_list_cap;
     a.slow_vis_slots = h->slow_vis_slots;
     a.slow_pass = 0;
+    a.pg = gb::PeerGather{};
+    if (pg) {
+        a.pg.n_peers = pg->n_peers;
+        a.pg.my_rank = pg->my_rank;
+        a.pg.row_offset = pg->row_offset;
+        a.pg.seq = pg->seq;
+        a.pg.done_counter = w->d_counters + 3;
+        for (uint32_t p = 0; p < pg->n_peers; ++p) {
+            a.pg.ids[p] = static_cast<uint32_t*>(pg->ids[p]);
+            a.pg.dists[p] = static_cast<float*>(pg->dists[p]);
+            a.pg.flags[p] = static_cast<unsigned int*>(pg->flags[p]);
+        }
+    }
     a.stg_rows = plan.stg_rows;
     a.stg_row_bytes = plan.stg_row_bytes;
     a.vis_global = nullptr;
@@ -901,12 +914,20 @@ int granne_b200_get_element(const granne_b200_index* hc, uint64_t idx, void* out
     return GRANNE_B200_OK;
 }
 
-int granne_b200_search_batch_device(granne_b200_index* h, const void* d_queries, size_t nq, int query_format,
-                                    uint32_t max_search, uint32_t num_neighbors, uint32_t* d_out_ids,
-                                    float* d_out_dists, uint32_t* d_out_counts, uint64_t* d_out_stats,
-                                    void* cuda_stream) {
-    int rc = validate_search(h, d_queries, nq, query_format, max_search, num_neighbors, d_out_ids, d_out_dists);
+static int search_device_impl(granne_b200_index* h, const void* d_queries, size_t nq, int query_format,
+                              uint32_t max_search, uint32_t num_neighbors, uint32_t* d_out_ids, float* d_out_dists,
+                              uint32_t* d_out_counts, uint64_t* d_out_stats, void* cuda_stream,
+                              const granne_b200_peer_gather* pg) {
+    int rc = validate_search(h, d_queries, nq, query_format, max_search, num_neighbors, pg ? (void*)pg : d_out_ids,
+                             pg ? (void*)pg : d_out_dists);
     if (rc) return rc;
+    if (pg) {
+        if (pg->n_peers < 1 || pg->n_peers > GRANNE_B200_MAX_PEERS || pg->my_rank >= pg->n_peers)
+            return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "peer gather: n_peers must be 1..8 and my_rank < n_peers");
+        for (uint32_t p = 0; p < pg->n_peers; ++p)
+            if (!pg->ids[p] || !pg->dists[p] || !pg->flags[p])
+                return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "peer gather: null peer pointer");
+    }
     if (nq == 0) return GRANNE_B200_OK;
     GB_CUDA(cudaSetDevice(h->device));
     cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
@@ -925,7 +946,24 @@ int granne_b200_search_batch_device(granne_b200_index* h, const void* d_queries,
         h->stream_ws[stream] = std::unique_ptr<Workspace>(w);
     }
     return enqueue_search(h, w, d_queries, nq, query_format, max_search, num_neighbors, d_out_ids, d_out_dists,
-                          d_out_counts, reinterpret_cast<unsigned long long*>(d_out_stats), stream, false);
+                          d_out_counts, reinterpret_cast<unsigned long long*>(d_out_stats), stream, false, pg);
+}
+
+int granne_b200_search_batch_device(granne_b200_index* h, const void* d_queries, size_t nq, int query_format,
+                                    uint32_t max_search, uint32_t num_neighbors, uint32_t* d_out_ids,
+                                    float* d_out_dists, uint32_t* d_out_counts, uint64_t* d_out_stats,
+                                    void* cuda_stream) {
+    return search_device_impl(h, d_queries, nq, query_format, max_search, num_neighbors, d_out_ids, d_out_dists,
+                              d_out_counts, d_out_stats, cuda_stream, nullptr);
+}
+
+int granne_b200_search_batch_device_gather(granne_b200_index* h, const void* d_queries, size_t nq, int query_format,
+                                           uint32_t max_search, uint32_t num_neighbors,
+                                           const granne_b200_peer_gather* gather, uint32_t* d_out_counts,
+                                           uint64_t* d_out_stats, void* cuda_stream) {
+    if (!gather) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "peer gather descriptor is null");
+    return search_device_impl(h, d_queries, nq, query_format, max_search, num_neighbors, nullptr, nullptr,
+                              d_out_counts, d_out_stats, cuda_stream, gather);
 }
 
 int granne_b200_stream_status(granne_b200_index* h) {

@@ -64,6 +64,22 @@ struct DeviceIndex {
     unsigned long long layer_len[kMaxLayers];
 };
 
+// Fused result gather (replicated index, queries sharded over GPUs): instead of leaving the tile in local memory for a
+// collective, the kernel stores every result row straight into the gathered buffer of EVERY peer (peer-mapped
+// memory over NVLink/NVSwitch; the own buffer is one of the entries) at row `row_offset + query`.  When all stores of
+// the launch are done, flags[p][my_rank] = seq is released system-wide so consumers on the peers can tell.
+constexpr int kMaxPeers = 8;
+struct PeerGather {
+    uint32_t* ids[kMaxPeers];
+    float* dists[kMaxPeers];
+    unsigned int* flags[kMaxPeers];
+    uint32_t n_peers;  // 0 = disabled (results go to out_ids / out_dists)
+    uint32_t my_rank;
+    unsigned long long row_offset;
+    unsigned int seq;
+    unsigned int* done_counter;
+};
+
 struct SearchArgs {
     const void* queries;  // nq x dim (f32 or i8)
     int query_format;
@@ -90,6 +106,7 @@ struct SearchArgs {
     uint32_t slow_list_cap;
     uint32_t slow_vis_slots;
     int slow_pass;  // 0: fast kernel, 1: slow kernel (processes only flagged queries)
+    PeerGather pg;
 };
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -1142,6 +1159,38 @@ __device__ __forceinline__ void prepare_query(const DeviceIndex& ix, const Searc
 // ------------------------------------------------------------------------------------------------------------------
 // Granne::search for a batch (src/index/mod.rs:140-150, 962-997): persistent warps over a work counter.
 // ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void store_result(const SearchArgs& a, unsigned long long qi, uint32_t k, uint32_t r,
+                                             uint32_t id, float d) {
+    if (a.pg.n_peers) {
+        const size_t o = (size_t)(a.pg.row_offset + qi) * k + r;
+#pragma unroll 1
+        for (uint32_t p = 0; p < a.pg.n_peers; ++p) {
+            a.pg.ids[p][o] = id;
+            a.pg.dists[p][o] = d;
+        }
+    } else {
+        a.out_ids[qi * k + r] = id;
+        a.out_dists[qi * k + r] = d;
+    }
+}
+
+// Called by every CTA of the LAST kernel of a search (the slow pass) before it exits: once all CTAs are through,
+// publish the sequence number to every peer.
+__device__ __forceinline__ void signal_peers(const SearchArgs& a, int lane) {
+    if (!a.pg.n_peers) return;
+    __threadfence_system();
+    __syncwarp();
+    if (lane == 0) {
+        const unsigned int old = atomicAdd(a.pg.done_counter, 1u);
+        if (old == gridDim.x - 1) {
+            __threadfence_system();
+            for (uint32_t p = 0; p < a.pg.n_peers; ++p)
+                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.pg.flags[p] + a.pg.my_rank), "r"(a.pg.seq)
+                             : "memory");
+        }
+    }
+}
+
 // R == 0: generic list (64-bit keys, any capacity, shared or global memory) — the slow pass and very large max_search.
 // R  > 0: fast list with capacity 32*R for the bottom layer (upper layers always use R = 1).
 template <class Dist, int R>
@@ -1194,7 +1243,10 @@ __global__ void __launch_bounds__(32, R > 0 ? 20 : 1) search_kernel(const Device
         }
     }
     Dist dist;
-    if (a.slow_pass && *reinterpret_cast<volatile unsigned int*>(a.overflow_seen) == 0u) return;  // nothing flagged
+    if (a.slow_pass && *reinterpret_cast<volatile unsigned int*>(a.overflow_seen) == 0u) {  // nothing flagged
+        signal_peers(a, c.lane);
+        return;
+    }
 
     while (true) {
         unsigned int qi0 = 0;
@@ -1247,10 +1299,7 @@ __global__ void __launch_bounds__(32, R > 0 ? 20 : 1) search_kernel(const Device
                         const bool fl = (j < n) && (v >> 63);
                         const unsigned m = __ballot_sync(kFullMask, fl);
                         const uint32_t rank = cnt + __popc(m & lanemask_lt());
-                        if (fl && rank < limit) {
-                            a.out_ids[qi * k + rank] = key_id(v);
-                            a.out_dists[qi * k + rank] = __uint_as_float(key_dbits(v));
-                        }
+                        if (fl && rank < limit) store_result(a, qi, k, rank, key_id(v), __uint_as_float(key_dbits(v)));
                         cnt += __popc(m);
                     }
                     found = cnt < limit ? cnt : limit;
@@ -1281,10 +1330,7 @@ __global__ void __launch_bounds__(32, R > 0 ? 20 : 1) search_kernel(const Device
                         const bool fl = (j < n) && (v >> 31);
                         const unsigned m = __ballot_sync(kFullMask, fl);
                         const uint32_t rank = cnt + __popc(m & lanemask_lt());
-                        if (fl && rank < limit) {
-                            a.out_ids[qi * k + rank] = Li[j];
-                            a.out_dists[qi * k + rank] = __uint_as_float(v & 0x7FFFFFFFu);
-                        }
+                        if (fl && rank < limit) store_result(a, qi, k, rank, Li[j], __uint_as_float(v & 0x7FFFFFFFu));
                         cnt += __popc(m);
                     }
                     found = cnt < limit ? cnt : limit;
@@ -1307,10 +1353,7 @@ __global__ void __launch_bounds__(32, R > 0 ? 20 : 1) search_kernel(const Device
             found = 0;
             if (c.lane == 0) atomicOr(a.error_flag, kStatusNotFinite);
         }
-        for (uint32_t r = found + c.lane; r < k; r += 32) {
-            a.out_ids[qi * k + r] = kUnusedId;
-            a.out_dists[qi * k + r] = __int_as_float(0x7f800000);
-        }
+        for (uint32_t r = found + c.lane; r < k; r += 32) store_result(a, qi, k, r, kUnusedId, __int_as_float(0x7f800000));
         if (c.lane == 0) {
             if (a.out_counts) a.out_counts[qi] = found;
             if (a.out_stats) {
@@ -1323,6 +1366,7 @@ __global__ void __launch_bounds__(32, R > 0 ? 20 : 1) search_kernel(const Device
             if (!(c.status & kStatusOverflow)) a.query_status[qi] = 0;
         }
     }
+    if (a.slow_pass) signal_peers(a, c.lane);
 }
 
 // ------------------------------------------------------------------------------------------------------------------

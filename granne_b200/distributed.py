@@ -109,6 +109,68 @@ class ReplicatedGranne:
         return ids[keep], dists[keep]
 
 
+class FusedGather:
+    """Peer-mapped gathered result buffers for mode 1 (replicated index): the search kernels store each rank's tile
+    straight into every rank's buffer over NVLink (granne_b200_search_batch_device_gather) — no collective per step.
+
+    `slots` independent buffers ([world * nq, k] ids + dists each) allow several steps in flight.  After a step,
+    flags(slot)[r] == seq tells that rank r's tile of that step has landed in THIS rank's buffer."""
+
+    def __init__(self, nq_local, k, slots=4, group=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+
+        from .api import PeerGather
+
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.nq, self.k, self.slots = nq_local, k, slots
+        dev = torch.device("cuda", torch.cuda.current_device())
+        rows = self.world * nq_local
+        self.tile = rows * k                       # int32 elements per ids (or dists) buffer
+        per_slot = 2 * self.tile + 32              # ids | dists | flags (padded)
+        self.buf = symm_mem.empty(slots * per_slot, dtype=torch.int32, device=dev)
+        self.buf.zero_()
+        self.hdl = symm_mem.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        ptrs = list(self.hdl.buffer_ptrs)
+        self.per_slot = per_slot
+        self._PeerGather = PeerGather
+        self.specs = []
+        for sl in range(slots):
+            g = PeerGather()
+            g.n_peers = self.world
+            g.my_rank = self.rank
+            g.row_offset = self.rank * nq_local
+            for p in range(self.world):
+                base = ptrs[p] + sl * per_slot * 4
+                g.ids[p] = base
+                g.dists[p] = base + self.tile * 4
+                g.flags[p] = base + 2 * self.tile * 4
+            self.specs.append(g)
+        torch.cuda.synchronize()
+        dist.barrier(group)
+
+    def spec(self, slot, seq):
+        g = self.specs[slot]
+        g.seq = seq
+        return g
+
+    def ids(self, slot):
+        o = slot * self.per_slot
+        return self.buf[o:o + self.tile].view(self.world * self.nq, self.k)
+
+    def dists(self, slot):
+        import torch
+
+        o = slot * self.per_slot + self.tile
+        return self.buf[o:o + self.tile].view(torch.float32).view(self.world * self.nq, self.k)
+
+    def flags(self, slot):
+        o = slot * self.per_slot + 2 * self.tile
+        return self.buf[o:o + self.world]
+
+
 class PartitionedGranne:
     """One independent index per contiguous id range (one per rank); all queries searched on every shard; per-shard
     tiles all-gathered and merged by (distance, global id)."""

@@ -138,6 +138,29 @@ int granne_b200_search_batch_device(granne_b200_index* h, const void* d_queries,
                                     float* d_out_dists, uint32_t* d_out_counts, uint64_t* d_out_stats,
                                     void* cuda_stream);
 
+/* Multi-GPU result gather fused into the search kernels (replicated index, query batch sharded over GPUs, SURVEY.md §8e
+ * mode 1).  `ids[p]` / `dists[p]` are device pointers, valid on THIS device, to the gathered result buffers of peer p
+ * (peer-mapped memory, e.g. torch symmetric memory or cudaIpc/cuMem mappings; entry `my_rank` is this GPU's own
+ * buffer), each [total_queries][num_neighbors].  The kernels store the rows of this call at row `row_offset + i` of
+ * every peer buffer over NVLink — no collective, no rendezvous — and, when every store is done, release
+ * `flags[p][my_rank] = seq` system-wide. */
+#define GRANNE_B200_MAX_PEERS 8
+typedef struct granne_b200_peer_gather {
+    uint32_t n_peers; /* 1..8 */
+    uint32_t my_rank;
+    uint64_t row_offset;
+    uint32_t seq;
+    uint32_t reserved;
+    void* ids[GRANNE_B200_MAX_PEERS];   /* u32 [total_queries][k] */
+    void* dists[GRANNE_B200_MAX_PEERS]; /* f32 [total_queries][k] */
+    void* flags[GRANNE_B200_MAX_PEERS]; /* u32 [n_peers] per peer */
+} granne_b200_peer_gather;
+/* granne_b200_search_batch_device with the results delivered through `gather` instead of d_out_ids/d_out_dists. */
+int granne_b200_search_batch_device_gather(granne_b200_index* h, const void* d_queries, size_t nq, int query_format,
+                                           uint32_t max_search, uint32_t num_neighbors,
+                                           const granne_b200_peer_gather* gather, uint32_t* d_out_counts,
+                                           uint64_t* d_out_stats, void* cuda_stream);
+
 /* After synchronising a stream used with granne_b200_search_batch_device: GRANNE_B200_OK, or the first error
  * (ERR_NOT_FINITE / ERR_CAPACITY) any query of the calls issued since the previous check raised. */
 int granne_b200_stream_status(granne_b200_index* h);

@@ -15,7 +15,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import granne_b200  # noqa: E402
-from granne_b200.distributed import PartitionedGranne, ReplicatedGranne, merge_topk_host  # noqa: E402
+from granne_b200.distributed import FusedGather, PartitionedGranne, ReplicatedGranne, merge_topk_host, shard_bounds  # noqa: E402
 from helpers.data import build_fixture, random_vectors  # noqa: E402
 from oracle import granne_oracle as go  # noqa: E402
 
@@ -41,6 +41,22 @@ def main():
     ref_ids, ref_d, _ = g.search_batch(q, 50, 10)
     assert np.array_equal(ids.cpu().numpy().view(np.uint32), ref_ids), "replicated ids"
     assert np.array_equal(d.cpu().numpy().view(np.uint32), ref_d.view(np.uint32)), "replicated dists"
+
+    # mode 1 with the fused gather: kernels store their tiles straight into every peer's buffer (no collective)
+    per = 128
+    fg = FusedGather(per, 10, slots=2)
+    for step in range(3):
+        lq = tq[rank * per:(rank + 1) * per]
+        idx.search_batch_device_gather(lq, fg.spec(step % 2, step + 1), 50, 10)
+    torch.cuda.synchronize()
+    idx.stream_status()
+    dist.barrier()
+    torch.cuda.synchronize()
+    gi = fg.ids(0).cpu().numpy().view(np.uint32)   # slot 0 holds step 2 (same queries every step)
+    gd = fg.dists(0).cpu().numpy()
+    assert np.array_equal(gi, ref_ids[:world * per]), "fused gather ids"
+    assert np.array_equal(gd.view(np.uint32), ref_d[:world * per].view(np.uint32)), "fused gather dists"
+    assert fg.flags(0).cpu().tolist() == [3] * world and fg.flags(1).cpu().tolist() == [2] * world, "gather flags"
 
     # mode 2: one index per contiguous id range
     sizes = [3000 + 500 * r for r in range(world)]
