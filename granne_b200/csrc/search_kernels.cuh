@@ -271,38 +271,20 @@ struct DistF32 {
         return p;
     }
 
-    // Starts the bulk copies of the first batch of candidate rows (lane b copies row b); `finish` waits for them.
-    __device__ __forceinline__ void issue(const DeviceIndex& ix, WarpCtx& c, uint32_t my_id, int k) {
-        if (FULL > 0) {
-            const uint32_t stride_bytes = ix.row_stride * 4u;
-            const uint32_t copy_bytes = FULL * 128u;  // the permuted chunk part of a row (multiple of 16)
-            const int rb = (int)c.stg_rows;
-            const int nb = k < rb ? k : rb;
-            __syncwarp();  // everyone is done reading the previous batch
-            if (c.lane == 0) mbar_arrive_expect_tx(c.bar, (uint32_t)nb * copy_bytes);
-            if (c.lane < nb)
-                bulk_copy_g2s(smem_u32(c.stg) + c.lane * copy_bytes,
-                              static_cast<const char*>(ix.vectors) + (size_t)my_id * stride_bytes, copy_bytes, c.bar,
-                              c.pol_stream);
-        }
-    }
-
-    __device__ __forceinline__ float finish(const DeviceIndex& ix, WarpCtx& c, uint32_t my_id, int k) {
+    __device__ __forceinline__ float dists(const DeviceIndex& ix, WarpCtx& c, uint32_t my_id, int k) {
         const uint32_t stride_bytes = ix.row_stride * 4u;
         if (FULL > 0) {
-            const uint32_t copy_bytes = FULL * 128u;
+            const uint32_t copy_bytes = FULL * 128u;  // the permuted chunk part of a row (multiple of 16)
             const int rb = (int)c.stg_rows;
             for (int j0 = 0; j0 < k; j0 += rb) {
                 const int nb = (k - j0) < rb ? (k - j0) : rb;
-                if (j0 > 0) {  // further batches are fetched synchronously
-                    const uint32_t id = __shfl_sync(kFullMask, my_id, (j0 + c.lane) & 31);
-                    __syncwarp();
-                    if (c.lane == 0) mbar_arrive_expect_tx(c.bar, (uint32_t)nb * copy_bytes);
-                    if (c.lane < nb)
-                        bulk_copy_g2s(smem_u32(c.stg) + c.lane * copy_bytes,
-                                      static_cast<const char*>(ix.vectors) + (size_t)id * stride_bytes, copy_bytes,
-                                      c.bar, c.pol_stream);
-                }
+                const uint32_t id = __shfl_sync(kFullMask, my_id, (j0 + c.lane) & 31);
+                __syncwarp();  // everyone is done reading the previous batch
+                if (c.lane == 0) mbar_arrive_expect_tx(c.bar, (uint32_t)nb * copy_bytes);
+                if (c.lane < nb)
+                    bulk_copy_g2s(smem_u32(c.stg) + c.lane * copy_bytes,
+                                  static_cast<const char*>(ix.vectors) + (size_t)id * stride_bytes, copy_bytes, c.bar,
+                                  c.pol_stream);
                 mbar_wait(c.bar, c.phase);
                 c.phase ^= 1u;
                 const unsigned char* mine = c.stg + c.lane * (V * 4);
@@ -340,20 +322,11 @@ struct DistF32 {
         __syncwarp();
         return d;
     }
-
-    __device__ __forceinline__ float dists(const DeviceIndex& ix, WarpCtx& c, uint32_t my_id, int k) {
-        issue(ix, c, my_id, k);
-        return finish(ix, c, my_id, k);
-    }
 };
 
 // ANGULAR f32, any dim (runtime chunk count; natural row layout; query read from shared memory).
 struct DistF32Generic {
     static constexpr bool kStaged = false;
-    __device__ __forceinline__ void issue(const DeviceIndex&, WarpCtx&, uint32_t, int) {}
-    __device__ __forceinline__ float finish(const DeviceIndex& ix, WarpCtx& c, uint32_t my_id, int k) {
-        return dists(ix, c, my_id, k);
-    }
     __device__ __forceinline__ void load_query(const DeviceIndex&, const WarpCtx&) {}
     __device__ __forceinline__ float dists(const DeviceIndex& ix, WarpCtx& c, uint32_t my_id, int k) {
         const float* base = static_cast<const float*>(ix.vectors);
@@ -390,18 +363,7 @@ struct DistF32Generic {
 struct DistI8 {
     static constexpr bool kStaged = true;
     __device__ __forceinline__ void load_query(const DeviceIndex&, const WarpCtx&) {}
-    __device__ __forceinline__ void issue(const DeviceIndex& ix, WarpCtx& c, uint32_t my_id, int k) {
-        const uint32_t stride = ix.row_stride;
-        const int rb = (int)c.stg_rows;
-        const int nb = k < rb ? k : rb;
-        __syncwarp();  // everyone is done reading the previous batch
-        if (c.lane == 0) mbar_arrive_expect_tx(c.bar, (uint32_t)nb * stride);
-        if (c.lane < nb)
-            bulk_copy_g2s(smem_u32(c.stg) + c.lane * stride, static_cast<const char*>(ix.vectors) + (size_t)my_id * stride,
-                          stride, c.bar, c.pol_stream);
-    }
-
-    __device__ __forceinline__ float finish(const DeviceIndex& ix, WarpCtx& c, uint32_t my_id, int k) {
+    __device__ __forceinline__ float dists(const DeviceIndex& ix, WarpCtx& c, uint32_t my_id, int k) {
         const uint32_t stride = ix.row_stride;
         const int words = stride / 4;
         const int* qw = reinterpret_cast<const int*>(c.qs);
@@ -409,15 +371,12 @@ struct DistI8 {
         const int rb = (int)c.stg_rows;
         for (int j0 = 0; j0 < k; j0 += rb) {
             const int nb = (k - j0) < rb ? (k - j0) : rb;
-            if (j0 > 0) {
-                const uint32_t id = __shfl_sync(kFullMask, my_id, (j0 + c.lane) & 31);
-                __syncwarp();
-                if (c.lane == 0) mbar_arrive_expect_tx(c.bar, (uint32_t)nb * stride);
-                if (c.lane < nb)
-                    bulk_copy_g2s(smem_u32(c.stg) + c.lane * stride,
-                                  static_cast<const char*>(ix.vectors) + (size_t)id * stride, stride, c.bar,
-                                  c.pol_stream);
-            }
+            const uint32_t id = __shfl_sync(kFullMask, my_id, (j0 + c.lane) & 31);
+            __syncwarp();  // everyone is done reading the previous batch
+            if (c.lane == 0) mbar_arrive_expect_tx(c.bar, (uint32_t)nb * stride);
+            if (c.lane < nb)
+                bulk_copy_g2s(smem_u32(c.stg) + c.lane * stride,
+                              static_cast<const char*>(ix.vectors) + (size_t)id * stride, stride, c.bar, c.pol_stream);
             mbar_wait(c.bar, c.phase);
             c.phase ^= 1u;
             for (int b = 0; b < nb; ++b) {
@@ -447,21 +406,12 @@ struct DistI8 {
         __syncwarp();
         return d;
     }
-
-    __device__ __forceinline__ float dists(const DeviceIndex& ix, WarpCtx& c, uint32_t my_id, int k) {
-        issue(ix, c, my_id, k);
-        return finish(ix, c, my_id, k);
-    }
 };
 
 // EMBEDDINGS: element = ordered sum of embedding rows, normalised, then the f32 angular distance
 // (src/elements/embeddings/mod.rs:124-143,164-174; src/math.rs:92-150).  Natural row layout, runtime dim.
 struct DistSum {
     static constexpr bool kStaged = false;
-    __device__ __forceinline__ void issue(const DeviceIndex&, WarpCtx&, uint32_t, int) {}
-    __device__ __forceinline__ float finish(const DeviceIndex& ix, WarpCtx& c, uint32_t my_id, int k) {
-        return dists(ix, c, my_id, k);
-    }
     __device__ __forceinline__ void load_query(const DeviceIndex&, const WarpCtx&) {}
 
     // materialises ElementContainer::get(id) into c.xs (all lanes participate)
@@ -850,7 +800,6 @@ __device__ __forceinline__ void search_layer_fast(const DeviceIndex& ix, WarpCtx
     constexpr uint32_t cap = 32u * R;
     constexpr uint32_t P = fast_list_pow2(R);  // Ld is padded to a power of two > cap with +inf-like sentinels
     constexpr uint32_t kFlag = 0x80000000u, kDMask = 0x7FFFFFFFu;
-    constexpr uint32_t kNone = 0xFFFFFFFFu;
     uint32_t* Ld = reinterpret_cast<uint32_t*>(c.list);
     uint32_t* Li = Ld + P;
     const int lane = c.lane;
@@ -883,135 +832,9 @@ __device__ __forceinline__ void search_layer_fast(const DeviceIndex& ix, WarpCtx
     }
     uint32_t n = 1, n_exp = 0, cursor = 0, pos_thr = 0, thr_bits = 0;
     uint32_t spec_id = kUnusedId, spec_nb = kUnusedId;
-    // Keys produced by the previous expansion (one per lane, `pend_pm` = lanes holding one).  They are merged into
-    // the list one step late — after the gather of the NEXT expansion's candidate rows has been issued — so that
-    // the merge (pure instruction work) overlaps the gather's memory latency.  The node to expand next is still
-    // chosen exactly: it is the minimum of the list's first unexpanded entry and the pending keys.
-    uint32_t pend_d = 0, pend_id = 0;
-    unsigned pend_pm = 0;
-
-    // Merges the pending keys.  `track_pos` (a list position, or kNone) / `track_lane` (a pending lane, or -1) name
-    // the entry that is about to be expanded; its position after the merge is returned in *tracked.
-    auto merge_pending = [&](uint32_t track_pos, int track_lane, uint32_t* tracked) -> bool {
-        const unsigned pm = pend_pm;
-        pend_pm = 0;
-        if (pm == 0) {
-            *tracked = track_pos;
-            return true;
-        }
-        const bool pass = (pm >> lane) & 1u;
-        const uint32_t my_d = pend_d, my_id = pend_id;
-        const uint32_t m = __popc(pm);
-        c.n_ins += m;
-        // rank of my key among the entries: branch-free lower bound on the distance over the padded array
-        // (entries at positions >= n are sentinels), refined by id on exact distance ties
-        uint32_t lo = 0;
-#pragma unroll
-        for (uint32_t step = P / 2; step >= 1; step >>= 1)
-            if ((Ld[lo + step - 1] & kDMask) < my_d) lo += step;
-        while (lo < n && (Ld[lo] & kDMask) == my_d && Li[lo] < my_id) ++lo;  // (d, id) tuple order
-        const uint32_t rank_l = lo;
-        // my entries (lane-major: lane l owns positions [R*l, R*l+R)) and how far each one moves:
-        // sh(j) = number of new keys ranked at or before entry j;  my key lands at rank_l + #smaller new keys
-        uint32_t dv[R], iv[R], sh[R];
-#pragma unroll
-        for (int t = 0; t < R; ++t) {
-            const uint32_t j = R * lane + t;
-            dv[t] = Ld[j];  // positions >= n hold sentinels (Ld is padded), Li is only read below n
-            iv[t] = j < n ? Li[j] : 0u;
-            sh[t] = 0;
-        }
-        uint32_t rank_n = 0, sh_base = 0;
-        for (unsigned t = pm; t; t &= t - 1) {
-            const int j = __ffs(t) - 1;
-            const uint32_t rj = __shfl_sync(kFullMask, rank_l, j);
-            const uint32_t dj = __shfl_sync(kFullMask, my_d, j);
-            const uint32_t ij = __shfl_sync(kFullMask, my_id, j);
-            rank_n += (dj < my_d || (dj == my_d && ij < my_id)) ? 1u : 0u;
-            // keys ranked before my first position shift all my entries; a key ranked inside my R positions
-            // (rare) shifts only the entries at or after it
-            const uint32_t rel = rj - (uint32_t)(R * lane);  // wraps to a huge value when rj < R*lane
-            if (rj <= (uint32_t)(R * lane)) {
-                sh_base += 1;
-            } else if (rel < (uint32_t)R) {
-#pragma unroll
-                for (int tt = 0; tt < R; ++tt) sh[tt] += (rel <= (uint32_t)tt) ? 1u : 0u;
-            }
-        }
-#pragma unroll
-        for (int tt = 0; tt < R; ++tt) sh[tt] += sh_base;
-        const uint32_t new_pos = rank_l + rank_n;
-        const uint32_t total = n + m;
-        uint32_t drop_flagged = 0;
-        if (track_lane >= 0) {
-            *tracked = __shfl_sync(kFullMask, new_pos, track_lane);
-        } else if (track_pos != kNone) {
-            *tracked = track_pos + __popc(__ballot_sync(kFullMask, pass && rank_l <= track_pos));
-        } else {
-            *tracked = kNone;
-        }
-        __syncwarp();  // every lane holds its entries in registers: the list can be rewritten in place
-#pragma unroll
-        for (int t = 0; t < R; ++t) {
-            const uint32_t j = R * lane + t;
-            if (j < n && sh[t] > 0) {
-                const uint32_t np = j + sh[t];
-                if (np < cap) {
-                    Ld[np] = dv[t];
-                    Li[np] = iv[t];
-                } else {
-                    drop_flagged += dv[t] >> 31;
-                }
-            }
-        }
-        if (pass && new_pos < cap) {
-            Ld[new_pos] = my_d;
-            Li[new_pos] = my_id;
-        }
-        __syncwarp();
-        if (total > cap) {
-            n = cap;
-            // entries fell off the end: legal only if >= ef strictly closer entries remain; everything dropped is
-            // >= the last kept entry, so "L[ef-1].d < L[cap-1].d" is sufficient (else: slow path)
-            if (!((Ld[ef - 1] & kDMask) < (Ld[cap - 1] & kDMask))) return false;
-            if (n_exp >= ef) {
-                if (pos_thr + m >= cap) {
-                    // res.peek() itself left L: res now spans evicted entries ("not full" regime); recount
-                    uint32_t cnt = 0;
-                    for (uint32_t base = 0; base < n; base += 32) {
-                        const uint32_t j = base + lane;
-                        cnt += __popc(__ballot_sync(kFullMask, (j < n) && (Ld[j] & kFlag)));
-                    }
-                    n_exp = cnt < ef ? cnt : ef - 1;
-                } else {
-                    pos_thr += m;
-                }
-            } else {
-                n_exp -= __reduce_add_sync(kFullMask, drop_flagged);
-            }
-        } else {
-            n = total;
-            if (n_exp >= ef) pos_thr += m;
-        }
-        return true;
-    };
 
     while (true) {
-        // Rare: merging the pending keys would push res.peek() out of the list, which changes whether res counts as
-        // full for the break test below -> merge first (no overlap for this expansion).
-        if (pend_pm && n_exp >= ef) {
-            const uint32_t m = __popc(pend_pm);
-            if (n + m > cap && pos_thr + m >= cap) {
-                uint32_t dummy;
-                if (!merge_pending(kNone, -1, &dummy)) {
-                    c.status |= kStatusOverflow;
-                    *out_n = n;
-                    return;
-                }
-                cursor = 0;
-            }
-        }
-        // ---- pq.pop(): minimum of (first unexpanded list entry at/after the cursor, pending keys) ----
+        // ---- pq.pop(): first unexpanded entry at or after the cursor; also find the runner-up ----
         int px = -1;
         uint32_t base_sel = cursor & ~31u;
         unsigned sel_mask = 0;
@@ -1024,27 +847,13 @@ __device__ __forceinline__ void search_layer_fast(const DeviceIndex& ix, WarpCtx
                 break;
             }
         }
-        uint32_t xd = kNone, xid = kUnusedId;
-        if (px >= 0) {
-            xd = Ld[px];  // unflagged
-            xid = Li[px];
-        }
-        int from_lane = -1;
-        if (pend_pm) {
-            const bool has = (pend_pm >> lane) & 1u;
-            const uint32_t bd = warp_min_u32(kFullMask, has ? pend_d : kNone);
-            const uint32_t bi = warp_min_u32(kFullMask, (has && pend_d == bd) ? pend_id : kNone);
-            if (px < 0 || bd < xd || (bd == xd && bi < xid)) {
-                from_lane = __ffs(__ballot_sync(kFullMask, has && pend_d == bd && pend_id == bi)) - 1;
-                xd = bd;
-                xid = bi;
-            }
-        }
-        if (px < 0 && from_lane < 0) break;             // pq empty
-        if (n_exp >= ef && xd > thr_bits) break;        // res.is_full() && d > res.peek().0  (:1019-1021)
-
-        // Speculation: load the adjacency row of the most likely NEXT expansion into a register now (one lane = one
-        // neighbour, width <= 32) so that its latency overlaps this whole expansion; a wrong guess costs one load.
+        if (px < 0) break;
+        const uint32_t xd = Ld[px];  // unflagged
+        const uint32_t xid = Li[px];
+        if (n_exp >= ef && xd > thr_bits) break;
+        // Speculation: the runner-up of this pop (next unexpanded entry of the same 32-entry row) is the most likely
+        // next expansion.  Its adjacency row is loaded into a register now (one lane = one neighbour, width <= 32)
+        // so that the load latency overlaps this whole expansion; a wrong guess only costs the load.
         uint32_t cur_nb = kUnusedId;
         const bool have_cur = (spec_id == xid) && (width <= 32u);
         if (have_cur) {
@@ -1052,31 +861,56 @@ __device__ __forceinline__ void search_layer_fast(const DeviceIndex& ix, WarpCtx
             c.n_spec += 1;
         }
         spec_id = kUnusedId;
-        if (width <= 32u) {
-            if (from_lane >= 0) {
-                if (px >= 0) spec_id = Li[px];  // the list's first unexpanded entry stays next in line
-            } else {
-                const unsigned rest = sel_mask & (sel_mask - 1);
-                if (rest) spec_id = Li[base_sel + __ffs(rest) - 1];
-            }
-            if (spec_id != kUnusedId)
+        {
+            const unsigned rest = sel_mask & (sel_mask - 1);
+            if (rest && width <= 32u) {
+                spec_id = Li[base_sel + __ffs(rest) - 1];
                 spec_nb = ((uint32_t)lane < width) ? __ldg(rows + (size_t)spec_id * width + lane) : kUnusedId;
+            }
+        }
+
+        // ---- res.push ----
+        __syncwarp();
+        if (lane == 0) Ld[px] = xd | kFlag;
+        __syncwarp();
+        cursor = px + 1;
+        n_exp += 1;
+        if (n_exp == ef) {
+            for (int base = (int)((n - 1) & ~31u); base >= 0; base -= 32) {
+                const uint32_t j = base + lane;
+                const unsigned m = __ballot_sync(kFullMask, (j < n) && (Ld[j] & kFlag));
+                if (m) {
+                    pos_thr = base + 31 - __clz(m);
+                    break;
+                }
+            }
+            thr_bits = Ld[pos_thr] & kDMask;
+        } else if (n_exp > ef) {
+            n_exp = ef;
+            if ((uint32_t)px < pos_thr) {
+                for (int base = (int)((pos_thr - 1) & ~31u); base >= 0; base -= 32) {
+                    const uint32_t j = base + lane;
+                    const unsigned m = __ballot_sync(kFullMask, (j < pos_thr) && (Ld[j] & kFlag));
+                    if (m) {
+                        pos_thr = base + 31 - __clz(m);
+                        break;
+                    }
+                }
+                thr_bits = Ld[pos_thr] & kDMask;
+            }
         }
         c.n_expand += 1;
 
-        // ---- for neighbor in layer.get_neighbors(idx) (:1025-1033), 32 ids per pass ----
+        // ---- neighbours ----
         const uint32_t* row = rows + (size_t)xid * width;
-        bool first_chunk = true;
-        for (uint32_t w0 = 0; w0 < width || first_chunk; w0 += 32) {
-            uint32_t nb = kUnusedId;
-            if (w0 < width) nb = have_cur ? cur_nb : ((w0 + lane < width) ? __ldg(row + w0 + lane) : kUnusedId);
+        for (uint32_t w0 = 0; w0 < width; w0 += 32) {
+            const uint32_t nb = have_cur ? cur_nb : ((w0 + lane < width) ? __ldg(row + w0 + lane) : kUnusedId);
             const bool valid = nb != kUnusedId;
             const unsigned vm = __ballot_sync(kFullMask, valid);
-            if (vm == 0 && !first_chunk) break;
+            if (vm == 0) break;
             c.n_nbr += __popc(vm);
             bool ovf = false;
-            bool is_new = false;
-            if (vm) is_new = vis_bucket_insert(c.visited, nbuckets, nb, valid, &ovf, c.pol_keep);
+            const bool is_new = vis_bucket_insert(c.visited, nbuckets, nb, valid, &ovf, c.pol_keep);
             const unsigned nm = __ballot_sync(kFullMask, is_new);
             const int k = __popc(nm);
             vis_count += k;
@@ -1085,63 +919,12 @@ __device__ __forceinline__ void search_layer_fast(const DeviceIndex& ix, WarpCtx
                 *out_n = n;
                 return;
             }
-            uint32_t my_id = 0;
-            if (k) {
-                if (is_new) c.ids[__popc(nm & lanemask_lt())] = nb;
-                __syncwarp();
-                my_id = c.ids[lane < k ? lane : 0];
-                c.n_dist += k;
-                dist.issue(ix, c, my_id, k);  // the candidate rows are now in flight ...
-            }
-            // ... while the keys of the previous expansion (or chunk) are merged into the list
-            uint32_t tracked = kNone;
-            const bool had_pending = pend_pm != 0;
-            if (!merge_pending(first_chunk && from_lane < 0 ? (uint32_t)px : kNone, first_chunk ? from_lane : -1,
-                               &tracked)) {
-                if (k) dist.finish(ix, c, my_id, k);  // drain the copies before leaving
-                c.status |= kStatusOverflow;
-                *out_n = n;
-                return;
-            }
-            if (first_chunk) {
-                // ---- res.push((d, idx)) (:1023; max_size_heap.rs:18-32): flag the entry, maintain res.peek() ----
-                const uint32_t pxn = tracked;
-                if (lane == 0) Ld[pxn] |= kFlag;
-                __syncwarp();
-                cursor = pxn + 1;
-                n_exp += 1;
-                if (n_exp == ef) {
-                    for (int base = (int)((n - 1) & ~31u); base >= 0; base -= 32) {
-                        const uint32_t j = base + lane;
-                        const unsigned m2 = __ballot_sync(kFullMask, (j < n) && (Ld[j] & kFlag));
-                        if (m2) {
-                            pos_thr = base + 31 - __clz(m2);
-                            break;
-                        }
-                    }
-                    thr_bits = Ld[pos_thr] & kDMask;
-                } else if (n_exp > ef) {
-                    n_exp = ef;
-                    if (pxn < pos_thr) {
-                        for (int base = (int)((pos_thr - 1) & ~31u); base >= 0; base -= 32) {
-                            const uint32_t j = base + lane;
-                            const unsigned m2 = __ballot_sync(kFullMask, (j < pos_thr) && (Ld[j] & kFlag));
-                            if (m2) {
-                                pos_thr = base + 31 - __clz(m2);
-                                break;
-                            }
-                        }
-                        thr_bits = Ld[pos_thr] & kDMask;
-                    }
-                }
-                first_chunk = false;
-            } else if (had_pending) {
-                // keys of an earlier 32-id chunk of this same expansion entered the list: they may sit before the
-                // cursor (a neighbour can be closer than the node being expanded)
-                cursor = 0;
-            }
             if (k == 0) continue;
-            const float d = dist.finish(ix, c, my_id, k);
+            if (is_new) c.ids[__popc(nm & lanemask_lt())] = nb;
+            __syncwarp();
+            const uint32_t my_id = c.ids[lane < k ? lane : 0];
+            c.n_dist += k;
+            const float d = dist.dists(ix, c, my_id, k);
             if (__any_sync(kFullMask, c.status & kStatusNotFinite)) {
                 c.status |= kStatusNotFinite;
                 *out_n = n;
@@ -1158,9 +941,100 @@ __device__ __forceinline__ void search_layer_fast(const DeviceIndex& ix, WarpCtx
             // a key strictly farther than the last entry of a full list has >= ef strictly closer entries before
             // it (cap > ef): it can never be expanded nor reported, so it need not enter the list at all
             if (n == cap) pass = pass && !(my_d > (Ld[cap - 1] & kDMask));
-            pend_pm = __ballot_sync(kFullMask, pass);
-            pend_d = my_d;
-            pend_id = my_id;
+            const unsigned pm = __ballot_sync(kFullMask, pass);
+            if (pm == 0) continue;
+            const uint32_t m = __popc(pm);
+            c.n_ins += m;
+
+            // rank of my key among the entries: branch-free lower bound on the distance over the padded array
+            // (entries at positions >= n are sentinels), refined by id on exact distance ties
+            uint32_t lo = 0;
+#pragma unroll
+            for (uint32_t step = P / 2; step >= 1; step >>= 1)
+                if ((Ld[lo + step - 1] & kDMask) < my_d) lo += step;
+            while (lo < n && (Ld[lo] & kDMask) == my_d && Li[lo] < my_id) ++lo;  // (d, id) tuple order
+            const uint32_t rank_l = lo;
+            // my entries (lane-major: lane l owns positions [R*l, R*l+R)) and how far each one moves:
+            // sh(j) = number of new keys ranked at or before entry j;  my key lands at rank_l + #smaller new keys
+            uint32_t dv[R], iv[R], sh[R];
+#pragma unroll
+            for (int t = 0; t < R; ++t) {
+                const uint32_t j = R * lane + t;
+                dv[t] = Ld[j];  // positions >= n hold sentinels (Ld is padded), Li is only read below n
+                iv[t] = j < n ? Li[j] : 0u;
+                sh[t] = 0;
+            }
+            uint32_t rank_n = 0, sh_base = 0;
+            for (unsigned t = pm; t; t &= t - 1) {
+                const int j = __ffs(t) - 1;
+                const uint32_t rj = __shfl_sync(kFullMask, rank_l, j);
+                const uint32_t dj = __shfl_sync(kFullMask, my_d, j);
+                const uint32_t ij = __shfl_sync(kFullMask, my_id, j);
+                rank_n += (dj < my_d || (dj == my_d && ij < my_id)) ? 1u : 0u;
+                // keys ranked before my first position shift all my entries; a key ranked inside my R positions
+                // (rare) shifts only the entries at or after it
+                const uint32_t rel = rj - (uint32_t)(R * lane);  // wraps to a huge value when rj < R*lane
+                if (rj <= (uint32_t)(R * lane)) {
+                    sh_base += 1;
+                } else if (rel < (uint32_t)R) {
+#pragma unroll
+                    for (int tt = 0; tt < R; ++tt) sh[tt] += (rel <= (uint32_t)tt) ? 1u : 0u;
+                }
+            }
+#pragma unroll
+            for (int tt = 0; tt < R; ++tt) sh[tt] += sh_base;
+            const uint32_t new_pos = rank_l + rank_n;
+            const uint32_t total = n + m;
+            uint32_t drop_flagged = 0;
+            __syncwarp();  // every lane holds its entries in registers: the list can be rewritten in place
+#pragma unroll
+            for (int t = 0; t < R; ++t) {
+                const uint32_t j = R * lane + t;
+                if (j < n && sh[t] > 0) {
+                    const uint32_t np = j + sh[t];
+                    if (np < cap) {
+                        Ld[np] = dv[t];
+                        Li[np] = iv[t];
+                    } else {
+                        drop_flagged += dv[t] >> 31;
+                    }
+                }
+            }
+            if (pass && new_pos < cap) {
+                Ld[new_pos] = my_d;
+                Li[new_pos] = my_id;
+            }
+            __syncwarp();
+            if (total > cap) {
+                n = cap;
+                // entries fell off the end: legal only if >= ef strictly closer entries remain; everything dropped is
+                // >= the last kept entry, so "L[ef-1].d < L[cap-1].d" is sufficient (else: slow path)
+                if (!((Ld[ef - 1] & kDMask) < (Ld[cap - 1] & kDMask))) {
+                    c.status |= kStatusOverflow;
+                    *out_n = n;
+                    return;
+                }
+                if (n_exp >= ef) {
+                    if (pos_thr + m >= cap) {
+                        // res.peek() itself left L: res now spans evicted entries ("not full" regime); recount
+                        uint32_t cnt = 0;
+                        for (uint32_t base = 0; base < n; base += 32) {
+                            const uint32_t j = base + lane;
+                            cnt += __popc(__ballot_sync(kFullMask, (j < n) && (Ld[j] & kFlag)));
+                        }
+                        n_exp = cnt < ef ? cnt : ef - 1;
+                    } else {
+                        pos_thr += m;
+                    }
+                } else {
+                    n_exp -= __reduce_add_sync(kFullMask, drop_flagged);
+                }
+            } else {
+                n = total;
+                if (n_exp >= ef) pos_thr += m;
+            }
+            const uint32_t min_pos = warp_min_u32(kFullMask, pass ? new_pos : 0xFFFFFFFFu);
+            if (min_pos < cursor) cursor = min_pos;
         }
     }
     *out_n = n;
