@@ -5,7 +5,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB = os.path.join(_HERE, "libgranne_b200.so")
+_LIB = os.environ.get("GRANNE_B200_LIB") or os.path.join(_HERE, "libgranne_b200.so")  # env: tuning variants
 
 ANGULAR, ANGULAR_INT, EMBEDDINGS = 0, 1, 2
 QUERY_RAW_F32, QUERY_ELEMENT = 0, 1

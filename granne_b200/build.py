@@ -19,6 +19,8 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC", "-shared",
     # no --use_fast_math, and contraction left to explicit __fmaf_rn/__fadd_rn intrinsics in the distance code
     "-fmad=false",
+    # ~55 kernel instantiations (distance engine x list width): optimise them in parallel
+    "--split-compile", "0",
 ]
 
 

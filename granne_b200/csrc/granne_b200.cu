@@ -319,7 +319,7 @@ LaunchPlan make_plan(const Handle* h, uint32_t max_search) {
     if (p.staged) {
         const uint32_t row_bytes = d.kind == gb::kAngularI8 ? d.row_stride : d.full * 128u;
         p.stg_row_bytes = row_bytes;
-        p.stg_rows = std::min<uint32_t>(16, std::max<uint32_t>(4, (4096u / row_bytes) & ~3u));
+        p.stg_rows = std::min<uint32_t>(16, std::max<uint32_t>(4, ((unsigned)GB_STG_BYTES / row_bytes) & ~3u));
         base = ((base + 127) & ~size_t(127)) + (size_t)p.stg_rows * row_bytes;
     }
     p.base_smem = base;

@@ -28,6 +28,13 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#ifndef GB_MIN_BLOCKS
+#define GB_MIN_BLOCKS 20  // resident one-warp CTAs per SM the fast kernel is register-limited to (tuning knob)
+#endif
+#ifndef GB_STG_BYTES
+#define GB_STG_BYTES 4096  // staging tile per warp for bulk-copied candidate rows (tuning knob)
+#endif
+
 namespace granne_b200 {
 
 constexpr int kMaxLayers = 24;
@@ -1194,7 +1201,7 @@ __device__ __forceinline__ void signal_peers(const SearchArgs& a, int lane) {
 // R == 0: generic list (64-bit keys, any capacity, shared or global memory) — the slow pass and very large max_search.
 // R  > 0: fast list with capacity 32*R for the bottom layer (upper layers always use R = 1).
 template <class Dist, int R>
-__global__ void __launch_bounds__(32, R > 0 ? 20 : 1) search_kernel(const DeviceIndex ix, const SearchArgs a) {
+__global__ void __launch_bounds__(32, R > 0 ? GB_MIN_BLOCKS : 1) search_kernel(const DeviceIndex ix, const SearchArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WarpCtx c;
     c.lane = threadIdx.x;
