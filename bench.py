@@ -42,7 +42,8 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=1_000_000)
+    ap.add_argument("--elements", dest="n", type=int, default=1_000_000,
+                    help="number of indexed elements (not --n: torchrun would claim that prefix)")
     ap.add_argument("--dim", type=int, default=128)
     ap.add_argument("--nq", type=int, default=1024, help="queries per step per GPU")
     ap.add_argument("--max-search", type=int, default=200)
@@ -188,7 +189,9 @@ def run_reference(a):
     t = time.time()
     g.search_batch(probe, a.max_search, a.k, threads=threads)
     rate = probe.shape[0] / max(time.time() - t, 1e-6)
-    per_step = int(max(64, min(a.nq, rate * 1.0)))  # bounded sample per step (~1 s)
+    # bounded sample per step: ~1 s, and at most ~60 s for the whole --steps/--warmup run
+    per_step_s = min(1.0, 60.0 / max(1, a.steps + a.warmup))
+    per_step = int(max(64, min(a.nq, rate * per_step_s)))
     for _ in range(a.warmup):
         g.search_batch(queries[:per_step], a.max_search, a.k, threads=threads)
     t0 = time.time()
