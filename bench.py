@@ -251,7 +251,9 @@ def main():
         builder = granne_b200.GranneBuilder(a.kind, elements_bytes, num_neighbors=a.num_neighbors, max_search=200,
                                             device=local)
         builder.build()
-        index_bytes = builder.index_bytes()
+        # very large single-GPU runs skip the host-side file image (only needed for the CPU baseline / replication)
+        big = a.n > 20_000_000 and world == 1
+        index_bytes = None if big else builder.index_bytes()
         if world == 1:
             index = builder.get_index()
         builder_launches = 0
@@ -486,7 +488,7 @@ def main():
         except Exception:
             traffic = None
     cpu = None
-    if world == 1:
+    if world == 1 and index_bytes is not None and a.cpu_seconds > 0:
         cpu = cpu_baseline(np.asarray(index_bytes).tobytes(), np.asarray(elements_bytes).tobytes(), q_host, a,
                            a.cpu_seconds)
     line = {

@@ -30,6 +30,7 @@ struct BuildArgs {
     int* locks;                 // one spin lock per node
     uint32_t stg_rows;
     uint32_t stg_row_bytes;
+    uint32_t tile_rows;
     unsigned int* work_counter;
     uint32_t num_nodes;         // prune pass: nodes in the layer
 };
@@ -165,12 +166,13 @@ __device__ __forceinline__ void connect_nodes(const DeviceIndex& ix, WarpCtx& c,
 
 template <class Dist>
 __device__ __forceinline__ void setup_ctx(const DeviceIndex& ix, WarpCtx& c, LinkScratch& s, unsigned char* smem_raw,
-                                          uint32_t stg_rows, uint32_t stg_row_bytes, uint32_t cand_cap) {
+                                          uint32_t stg_rows, uint32_t stg_row_bytes, uint32_t tile_rows,
+                                          uint32_t cand_cap) {
     c.lane = threadIdx.x;
     unsigned char* sp = smem_raw;
     c.tile = reinterpret_cast<float*>(sp);
-    c.ids = reinterpret_cast<uint32_t*>(sp + 32 * kTileStride * sizeof(float));
-    sp += kTileBytes;
+    c.ids = reinterpret_cast<uint32_t*>(sp + tile_rows * kTileStride * sizeof(float));
+    sp += tile_bytes_for_rows(tile_rows);
     c.bar = smem_u32(sp);
     c.phase = 0;
     c.pol_stream = make_policy_evict_first();
@@ -215,7 +217,7 @@ __global__ void __launch_bounds__(32) build_link_kernel(const DeviceIndex ix, co
     WarpCtx c;
     LinkScratch s;
     const uint32_t cand_cap = a.cand_stride > 40 ? a.cand_stride : 40;
-    setup_ctx<Dist>(ix, c, s, smem_raw, a.stg_rows, a.stg_row_bytes, cand_cap);
+    setup_ctx<Dist>(ix, c, s, smem_raw, a.stg_rows, a.stg_row_bytes, a.tile_rows, cand_cap);
     Dist dist;
     const int lane = c.lane;
     while (true) {
@@ -287,7 +289,7 @@ __global__ void __launch_bounds__(32) build_prune_kernel(const DeviceIndex ix, c
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WarpCtx c;
     LinkScratch s;
-    setup_ctx<Dist>(ix, c, s, smem_raw, a.stg_rows, a.stg_row_bytes, 40);
+    setup_ctx<Dist>(ix, c, s, smem_raw, a.stg_rows, a.stg_row_bytes, a.tile_rows, 40);
     Dist dist;
     while (true) {
         unsigned int w0 = 0;

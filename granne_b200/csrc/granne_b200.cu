@@ -285,6 +285,7 @@ struct LaunchPlan {
     int rows;           // fast list rows R (capacity 32*R), 0 = generic list
     uint32_t stg_rows;  // candidate rows per bulk-copy batch (staged distance engines only)
     uint32_t stg_row_bytes;
+    uint32_t tile_rows;  // ordered-sum tile rows: 8 staged f32, 32 generic f32, 0 for i8 / embeddings
     size_t base_smem;   // tile + mbarrier + query (+ embeddings scratch) + staging
     size_t smem;        // fast pass total
     bool staged;
@@ -312,14 +313,16 @@ LaunchPlan make_plan(const Handle* h, uint32_t max_search) {
     uint64_t want = std::max<uint64_t>(1024, (uint64_t)max_search * std::min<uint32_t>(deg, 64));
     want = (want + 31) & ~31ull;
     const uint32_t qbytes = (d.kind == gb::kAngularI8) ? d.row_stride : ((d.dim + 3u) & ~3u) * 4u;
-    size_t base = gb::kTileBytes + 16 + ((qbytes + 15u) & ~15u) * (d.kind == gb::kSumEmbeddings ? 2 : 1);
     p.staged = is_staged_kind(d);
+    p.tile_rows = d.kind != gb::kAngularF32 ? 0u : (p.staged ? 8u : 32u);
+    size_t base = gb::tile_bytes_for_rows(p.tile_rows) + 16 + ((qbytes + 15u) & ~15u) * (d.kind == gb::kSumEmbeddings ? 2 : 1);
     p.stg_rows = 0;
     p.stg_row_bytes = 0;
     if (p.staged) {
         const uint32_t row_bytes = d.kind == gb::kAngularI8 ? d.row_stride : d.full * 128u;
         p.stg_row_bytes = row_bytes;
-        p.stg_rows = std::min<uint32_t>(16, std::max<uint32_t>(4, ((unsigned)GB_STG_BYTES / row_bytes) & ~3u));
+        p.stg_rows = std::min<uint32_t>(d.kind == gb::kAngularI8 ? 16u : 8u,
+                                        std::max<uint32_t>(4, ((unsigned)GB_STG_BYTES / row_bytes) & ~3u));
         base = ((base + 127) & ~size_t(127)) + (size_t)p.stg_rows * row_bytes;
     }
     p.base_smem = base;
@@ -577,6 +580,7 @@ int enqueue_search(Handle* h, Workspace* w, const void* d_queries, size_t nq, in
     }
     a.stg_rows = plan.stg_rows;
     a.stg_row_bytes = plan.stg_row_bytes;
+    a.tile_rows = plan.tile_rows;
     a.vis_global = nullptr;
     return dispatch_search(h, w, a, plan, stream);
 }
@@ -726,6 +730,7 @@ int builder_index_elements(Builder* b, uint32_t layer_m, uint32_t ef, uint64_t a
         L.a.locks = b->d_locks;
         L.a.stg_rows = plan.stg_rows;
         L.a.stg_row_bytes = plan.stg_row_bytes;
+        L.a.tile_rows = plan.tile_rows;
         L.a.work_counter = b->d_counter;
         L.a.num_nodes = (uint32_t)num;
         L.grid = (unsigned)std::min<uint64_t>(bsz, (uint64_t)h->num_sms * 8);
@@ -741,6 +746,7 @@ int builder_index_elements(Builder* b, uint32_t layer_m, uint32_t ef, uint64_t a
     P.a.max_neighbors = layer_m;
     P.a.stg_rows = plan.stg_rows;
     P.a.stg_row_bytes = plan.stg_row_bytes;
+    P.a.tile_rows = plan.tile_rows;
     P.a.work_counter = b->d_counter;
     P.a.num_nodes = (uint32_t)num;
     P.grid = (unsigned)std::min<uint64_t>(num, (uint64_t)h->num_sms * 8);

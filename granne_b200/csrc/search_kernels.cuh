@@ -43,7 +43,8 @@ constexpr unsigned long long kFlagExpanded = 1ull << 63;
 constexpr unsigned long long kKeyMask = ~kFlagExpanded;
 constexpr unsigned kFullMask = 0xFFFFFFFFu;
 constexpr int kTileStride = 36;  // floats per tile row: 16-byte aligned rows, conflict-free LDS.128 per quarter warp
-constexpr int kTileBytes = 32 * kTileStride * 4 + 128;  // tile + 32 x u32 id scratch
+constexpr int kIdScratchBytes = 128;  // 32 x u32 scratch for compacting candidate ids
+__host__ __device__ constexpr uint32_t tile_bytes_for_rows(uint32_t rows) { return rows * kTileStride * 4u + kIdScratchBytes; }
 
 enum ElementKind : int { kAngularF32 = 0, kAngularI8 = 1, kSumEmbeddings = 2 };
 enum QueryFormat : int { kQueryRawF32 = 0, kQueryElement = 1, kQueryById = 2 };  // ById: builder only (u32 ids)
@@ -99,6 +100,7 @@ struct SearchArgs {
     uint32_t* vis_global;     // fast pass: one table of vis_slots u32 per CTA in global memory (L2 resident)
     uint32_t stg_rows;        // candidate rows per bulk-copy batch (0 = this element kind loads directly)
     uint32_t stg_row_bytes;   // bytes of one staged row (f32: 128*FULL, i8: row_stride)
+    uint32_t tile_rows;       // rows of the ordered-sum tile (8 for the staged f32 engine, 32 generic, 0 unused)
     uint32_t* out_ids;
     float* out_dists;
     uint32_t* out_counts;
@@ -278,14 +280,41 @@ struct DistF32 {
         return p;
     }
 
-    __device__ __forceinline__ float dists(const DeviceIndex& ix, WarpCtx& c, uint32_t my_id, int k) {
-        const uint32_t stride_bytes = ix.row_stride * 4u;
+    // The ordered 32-lane sum (math.rs:27-30) and the FMA tail (:32-39) for candidate `id`, whose lane partials sit
+    // in tile row `trow` (ignored when FULL == 0).
+    __device__ __forceinline__ float ordered_finish(const DeviceIndex& ix, WarpCtx& c, uint32_t id, int trow) const {
+        float r = 0.0f;
         if (FULL > 0) {
+            const float4* t = reinterpret_cast<const float4*>(c.tile + trow * kTileStride);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float4 v = t[i];
+                r = __fadd_rn(r, v.x);
+                r = __fadd_rn(r, v.y);
+                r = __fadd_rn(r, v.z);
+                r = __fadd_rn(r, v.w);
+            }
+        }
+        const int tail = ix.tail;
+        if (tail) {
+            const float* row = reinterpret_cast<const float*>(static_cast<const char*>(ix.vectors) +
+                                                               (size_t)id * (ix.row_stride * 4u)) + FULL * 32;
+            const float* qt = c.qs + FULL * 32;
+            for (int t = 0; t < tail; ++t) r = __fmaf_rn(__ldg(row + t), qt[t], r);
+        }
+        return finish_angular(r, &c.status);
+    }
+
+    // Batches of up to stg_rows (<= 8 = tile rows) candidates: gather, lane partials into the tile, ordered sums.
+    __device__ __forceinline__ float dists(const DeviceIndex& ix, WarpCtx& c, uint32_t my_id, int k) {
+        float d = 0.0f;
+        if (FULL > 0) {
+            const uint32_t stride_bytes = ix.row_stride * 4u;
             const uint32_t copy_bytes = FULL * 128u;  // the permuted chunk part of a row (multiple of 16)
             const int rb = (int)c.stg_rows;
             for (int j0 = 0; j0 < k; j0 += rb) {
                 const int nb = (k - j0) < rb ? (k - j0) : rb;
-                const uint32_t id = __shfl_sync(kFullMask, my_id, (j0 + c.lane) & 31);
+                const uint32_t id = __shfl_sync(kFullMask, my_id, (j0 + c.lane) & 31);  // lane t: candidate j0 + t
                 __syncwarp();  // everyone is done reading the previous batch
                 if (c.lane == 0) mbar_arrive_expect_tx(c.bar, (uint32_t)nb * copy_bytes);
                 if (c.lane < nb)
@@ -297,34 +326,17 @@ struct DistF32 {
                 const unsigned char* mine = c.stg + c.lane * (V * 4);
                 for (int b = 0; b < nb; b += 4) {  // rows past nb hold stale data: computed, never used
 #pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        c.tile[(j0 + b + u) * kTileStride + c.lane] = partial(mine + (b + u) * copy_bytes);
+                    for (int u = 0; u < 4; ++u) c.tile[(b + u) * kTileStride + c.lane] = partial(mine + (b + u) * copy_bytes);
                 }
+                __syncwarp();
+                float db = 0.0f;
+                if (c.lane < nb) db = ordered_finish(ix, c, id, c.lane);
+                // hand the distance of candidate j0 + t (computed by lane t) to lane j0 + t
+                const float dj = __shfl_sync(kFullMask, db, (c.lane - j0) & 31);
+                if (c.lane >= j0 && c.lane < j0 + nb) d = dj;
             }
-            __syncwarp();
-        }
-        float d = 0.0f;
-        if (c.lane < k) {
-            float r = 0.0f;
-            if (FULL > 0) {
-                const float4* t = reinterpret_cast<const float4*>(c.tile + c.lane * kTileStride);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float4 v = t[i];
-                    r = __fadd_rn(r, v.x);
-                    r = __fadd_rn(r, v.y);
-                    r = __fadd_rn(r, v.z);
-                    r = __fadd_rn(r, v.w);
-                }
-            }
-            const int tail = ix.tail;
-            if (tail) {
-                const float* row = reinterpret_cast<const float*>(static_cast<const char*>(ix.vectors) +
-                                                                   (size_t)my_id * stride_bytes) + FULL * 32;
-                const float* qt = c.qs + FULL * 32;
-                for (int t = 0; t < tail; ++t) r = __fmaf_rn(__ldg(row + t), qt[t], r);
-            }
-            d = finish_angular(r, &c.status);
+        } else if (c.lane < k) {
+            d = ordered_finish(ix, c, my_id, 0);
         }
         __syncwarp();
         return d;
@@ -1209,8 +1221,8 @@ __global__ void __launch_bounds__(32, R > 0 ? GB_MIN_BLOCKS : 1) search_kernel(c
     //                                                          ... | list | visited (generic pass, slow_pass == 0)
     unsigned char* sp = smem_raw;
     c.tile = reinterpret_cast<float*>(sp);
-    c.ids = reinterpret_cast<uint32_t*>(sp + 32 * kTileStride * sizeof(float));
-    sp += kTileBytes;
+    c.ids = reinterpret_cast<uint32_t*>(sp + a.tile_rows * kTileStride * sizeof(float));
+    sp += tile_bytes_for_rows(a.tile_rows);
     c.bar = smem_u32(sp);
     c.phase = 0;
     c.pol_stream = make_policy_evict_first();
