@@ -61,6 +61,7 @@ struct Workspace {
     // slow path
     unsigned long long* d_slow_list = nullptr;
     uint32_t* d_slow_vis = nullptr;
+    size_t slow_vis_cap = 0;  // u32 entries allocated for d_slow_vis
     // fast pass: per-CTA visited tables in global memory
     uint32_t* d_vis = nullptr;
     size_t vis_cap = 0;  // u32 entries
@@ -449,7 +450,8 @@ int ws_acquire(Handle* h, Workspace** out) {
     GB_CUDA(cudaMalloc(&w->d_counters, 4 * sizeof(unsigned int)));
     GB_CUDA(cudaMalloc(&w->d_error, 4 * sizeof(int)));
     GB_CUDA(cudaMalloc(&w->d_slow_list, (size_t)h->slow_ctas * h->slow_list_cap * 8));
-    GB_CUDA(cudaMalloc(&w->d_slow_vis, (size_t)h->slow_ctas * h->slow_vis_slots * 4));
+    w->slow_vis_cap = (size_t)h->slow_ctas * h->slow_vis_slots;
+    GB_CUDA(cudaMalloc(&w->d_slow_vis, w->slow_vis_cap * 4));
     *out = w.release();
     return GRANNE_B200_OK;
 }
@@ -540,6 +542,15 @@ int enqueue_search(Handle* h, Workspace* w, const void* d_queries, size_t nq, in
         return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "max_search exceeds the supported maximum (about 27000)");
     int rc = ws_reserve_status(w, nq);
     if (rc) return rc;
+    // the slow-path visited tables follow the index size (a builder's index grows after its workspace was made)
+    if ((size_t)h->slow_ctas * h->slow_vis_slots > w->slow_vis_cap) {
+        GB_CUDA(cudaStreamSynchronize(stream));
+        cudaFree(w->d_slow_vis);
+        w->d_slow_vis = nullptr;
+        w->slow_vis_cap = 0;
+        GB_CUDA(cudaMalloc(&w->d_slow_vis, (size_t)h->slow_ctas * h->slow_vis_slots * 4));
+        w->slow_vis_cap = (size_t)h->slow_ctas * h->slow_vis_slots;
+    }
     GB_CUDA(cudaMemsetAsync(w->d_counters, 0, 4 * sizeof(unsigned int), stream));
     if (reset_error) GB_CUDA(cudaMemsetAsync(w->d_error, 0, 4 * sizeof(int), stream));
     GB_CUDA(cudaMemsetAsync(w->d_status, 0xFF, nq * sizeof(int), stream));

@@ -1248,7 +1248,7 @@ __global__ void __launch_bounds__(32, R > 0 ? GB_MIN_BLOCKS : 1) search_kernel(c
         c.visited = a.slow_visited + (size_t)blockIdx.x * a.slow_vis_slots;
         list_cap = a.slow_list_cap;
         vis_slots = a.slow_vis_slots;
-        vis_upper = a.slow_vis_slots;
+        vis_upper = a.slow_vis_slots < (1u << 16) ? a.slow_vis_slots : (1u << 16);  // max_search = 1 descents stay small
     } else {
         c.list = reinterpret_cast<unsigned long long*>(sp);
         list_cap = a.list_cap;
