@@ -122,16 +122,19 @@ def test_recall_against_brute_force():
 
 
 def test_builder_queries_that_overflow_the_fast_path():
-    # A tiny max_search makes the per-warp visited table tiny (max_search x degree slots): insertions regularly exceed
-    # it and take the slow pass while the index under construction keeps growing (regression: the slow-path buffers
-    # must follow the index size, not the size at the time the builder was created).
-    raw = clustered_vectors(30_000, 32, seed=11)
+    # Uniform random vectors have little neighbourhood overlap, so a search visits almost max_search x degree nodes and
+    # regularly exceeds the per-warp visited table: those insertions / queries take the slow pass while the index under
+    # construction keeps growing (regression: the slow-path buffers must follow the index size, not the size at the
+    # time the builder's workspace was created).
+    raw = random_vectors(30_000, 64, seed=11)
     eb = granne_b200.elements_from_raw("angular", raw).tobytes()
-    b = granne_b200.GranneBuilder("angular", eb, num_neighbors=31, max_search=33)
+    b = granne_b200.GranneBuilder("angular", eb, num_neighbors=31, max_search=40)
     b.build()
     index = b.get_index()
-    rows = np.frombuffer(eb, dtype=np.float32, offset=8).reshape(30_000, 32)
-    assert _self_recall(index, rows[:3000], 33) > 0.9
-    ids, d, c, st = index.search_batch(raw[:2000], 33, 10, with_stats=True)
+    ids, d, c, st = index.search_batch(random_vectors(2000, 64, seed=12), 40, 10, with_stats=True)
+    assert (c == 10).all()
+    assert int((st[:, 3] & 1).sum()) > 0  # the slow pass really is exercised with these parameters
+    rows = np.frombuffer(eb, dtype=np.float32, offset=8).reshape(30_000, 64)
+    assert _self_recall(index, rows[:3000], 40) > 0.9
     index.close()
     b.close()
