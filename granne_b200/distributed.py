@@ -12,8 +12,9 @@ range (the reference's own notion of sharding, src/elements/embeddings/parsing.r
 queries on its shard, the per-shard tiles are all-gathered and merged per query by (distance, global id) — the tuple
 order of into_sorted_vec (src/index/mod.rs:1036).  The merge runs on the GPU (granne_b200_merge_topk_device).
 
-The collective calls work on whatever backend the process group uses; on CPU tensors (gloo, used by the host-logic
-tests) the merge uses merge_topk_host below, which is the numpy statement of the same k-way merge.
+The collective calls work on whatever backend the process group uses.  The product path merges on the GPU; only the
+host-logic tests (gloo, CPU tensors, `host_merge=True`) use merge_topk_host below, the numpy statement of the same
+k-way merge.
 """
 import numpy as np
 
@@ -175,10 +176,11 @@ class PartitionedGranne:
     """One independent index per contiguous id range (one per rank); all queries searched on every shard; per-shard
     tiles all-gathered and merged by (distance, global id)."""
 
-    def __init__(self, index=None, shard_base=0, group=None, local_search=None, device_index=0):
+    def __init__(self, index=None, shard_base=0, group=None, local_search=None, device_index=0, host_merge=False):
         import torch
         import torch.distributed as dist
 
+        self.host_merge = host_merge  # tests only: merge CPU tensors (gloo) with merge_topk_host
         self.dist = dist
         self.group = group
         self.index = index
@@ -214,5 +216,8 @@ class PartitionedGranne:
             from .api import merge_topk_device
 
             return merge_topk_device(self.device_index, all_ids, all_d, self.bases)
+        if not self.host_merge:
+            raise RuntimeError("PartitionedGranne merges on the GPU; CPU tensors are only accepted with "
+                               "host_merge=True (host-logic tests over gloo)")
         gi, gd = merge_topk_host(all_ids.numpy().view(np.uint32), all_d.numpy(), self.bases, k)
         return torch.from_numpy(gi), torch.from_numpy(gd)

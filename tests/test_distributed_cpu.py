@@ -76,7 +76,7 @@ def _worker(rank, world, port, mode, ret):
                 ids, d, c = mine.search_batch(queries.numpy(), ef, k)
                 return torch.from_numpy(ids.view(np.int32)), torch.from_numpy(d)
 
-            p = PartitionedGranne(shard_base=base[rank], local_search=local)
+            p = PartitionedGranne(shard_base=base[rank], local_search=local, host_merge=True)
             gi, gd = p.search_batch(torch.from_numpy(q), 30, 10)
             parts = [s.search_batch(q, 30, 10) for s in shards]
             ei, ed = merge_topk_host(np.stack([x[0] for x in parts]), np.stack([x[1] for x in parts]), base, 10)
