@@ -185,10 +185,13 @@ __device__ __forceinline__ void setup_ctx(const DeviceIndex& ix, WarpCtx& c, Lin
     if (ix.kind == kSumEmbeddings) sp += (qbytes + 15u) & ~15u;
     c.stg = nullptr;
     c.stg_rows = stg_rows;
-    if (Dist::kStaged) {
+    c.stg_row_bytes = stg_row_bytes;
+    if (stg_rows) {
         sp = smem_raw + (((size_t)(sp - smem_raw) + 127u) & ~(size_t)127u);
         c.stg = sp;
         sp += (size_t)stg_rows * stg_row_bytes;
+    }
+    if (Dist::kStaged) {
         if (c.lane == 0) mbar_init(c.bar, 1);
         __syncwarp();
     }

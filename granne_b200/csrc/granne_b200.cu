@@ -315,10 +315,16 @@ LaunchPlan make_plan(const Handle* h, uint32_t max_search) {
     want = (want + 31) & ~31ull;
     const uint32_t qbytes = (d.kind == gb::kAngularI8) ? d.row_stride : ((d.dim + 3u) & ~3u) * 4u;
     p.staged = is_staged_kind(d);
-    p.tile_rows = d.kind != gb::kAngularF32 ? 0u : (p.staged ? 8u : 32u);
+    p.tile_rows = d.kind == gb::kAngularI8 ? 0u : ((p.staged || d.kind == gb::kSumEmbeddings) ? 8u : 32u);
     size_t base = gb::tile_bytes_for_rows(p.tile_rows) + 16 + ((qbytes + 15u) & ~15u) * (d.kind == gb::kSumEmbeddings ? 2 : 1);
     p.stg_rows = 0;
     p.stg_row_bytes = 0;
+    if (d.kind == gb::kSumEmbeddings) {
+        // staging tile = the summed vectors of a batch of candidates (one row each)
+        p.stg_row_bytes = ((d.dim + 3u) & ~3u) * 4u;
+        p.stg_rows = std::min<uint32_t>(8u, std::max<uint32_t>(4, (8192u / p.stg_row_bytes) & ~3u));
+        base = ((base + 127) & ~size_t(127)) + (size_t)p.stg_rows * p.stg_row_bytes;
+    }
     if (p.staged) {
         const uint32_t row_bytes = d.kind == gb::kAngularI8 ? d.row_stride : d.full * 128u;
         p.stg_row_bytes = row_bytes;

@@ -176,6 +176,7 @@ struct WarpCtx {
     float* xs;         // EMBEDDINGS scratch f32[dim], shared
     unsigned char* stg;  // staging tile for bulk-copied candidate rows (shared, 128-byte aligned)
     uint32_t stg_rows;   // rows that fit in the staging tile (<= 16)
+    uint32_t stg_row_bytes;
     uint32_t bar;        // shared-space address of the mbarrier the bulk copies signal
     uint32_t phase;      // its current phase parity
     unsigned long long pol_stream;  // L2 policy evict_first: candidate rows are read once per query
@@ -468,20 +469,90 @@ struct DistSum {
         __syncwarp();
     }
 
-    __device__ __forceinline__ float dists(const DeviceIndex& ix, WarpCtx& c, uint32_t my_id, int k) {
-        const int dim = ix.dim, full = ix.full;
-        float d = 0.0f;
-        for (int j = 0; j < k; ++j) {
-            const uint32_t id = __shfl_sync(kFullMask, my_id, j);
-            materialise(ix, c, id);
-            float p = 0.0f;
-            for (int ch = 0; ch < full; ++ch) p = __fmaf_rn(c.xs[ch * 32 + c.lane], c.qs[ch * 32 + c.lane], p);
-            float r = ordered_lane_sum_bcast(p);
-            for (int t = full * 32; t < dim; ++t) r = __fmaf_rn(c.xs[t], c.qs[t], r);
-            const float dj = finish_angular(r, &c.status);
-            if (c.lane == j) d = dj;
-            __syncwarp();
+    // Ordered 32-lane sum of tile row `trow` (math.rs:27-30) followed by the FMA tail over x[t]*y[t] (:32-39).
+    static __device__ __forceinline__ float ordered_dot(const WarpCtx& c, int trow, const float* x, const float* y,
+                                                        int full, int dim) {
+        float r = 0.0f;
+        const float4* t = reinterpret_cast<const float4*>(c.tile + trow * kTileStride);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float4 v = t[i];
+            r = __fadd_rn(r, v.x);
+            r = __fadd_rn(r, v.y);
+            r = __fadd_rn(r, v.z);
+            r = __fadd_rn(r, v.w);
         }
+        for (int e = full * 32; e < dim; ++e) r = __fmaf_rn(x[e], y[e], r);
+        return r;
+    }
+
+    // Batches of up to stg_rows candidates: their summed vectors live in the staging tile (row b = candidate b), the
+    // lane partials of the two dot products (norm, distance) go through the 8-row tile so that the strictly ordered
+    // 32-lane sums of a whole batch run in parallel (lane b sums candidate b) instead of two 32-step shuffle chains
+    // per candidate.
+    __device__ __forceinline__ float dists(const DeviceIndex& ix, WarpCtx& c, uint32_t my_id, int k) {
+        const float* emb = static_cast<const float*>(ix.vectors);
+        const size_t stride = ix.row_stride;
+        const int dim = ix.dim, full = ix.full;
+        const int xstride = (int)(c.stg_row_bytes / 4u);
+        float* X = reinterpret_cast<float*>(c.stg);
+        const int rb = (int)c.stg_rows;
+        float d = 0.0f;
+        for (int j0 = 0; j0 < k; j0 += rb) {
+            const int nb = (k - j0) < rb ? (k - j0) : rb;
+            const uint32_t idl = __shfl_sync(kFullMask, my_id, (j0 + c.lane) & 31);  // lane t: candidate j0 + t
+            __syncwarp();
+            // get_embedding_internal (embeddings/mod.rs:124-143): ordered sum of the term rows, element-wise
+            for (int b = 0; b < nb; ++b) {
+                const uint32_t id = __shfl_sync(kFullMask, idl, b);
+                const unsigned long long tb = ix.sum_offsets[id], te = ix.sum_offsets[id + 1];
+                float* xb = X + b * xstride;
+                for (int i = c.lane; i < dim; i += 32) {
+                    float x = 0.0f;
+                    if (tb < te) {
+                        x = __ldg(emb + (size_t)ix.sum_terms[tb] * stride + i);
+                        for (unsigned long long t = tb + 1; t < te; ++t)
+                            x = __fadd_rn(x, __ldg(emb + (size_t)ix.sum_terms[t] * stride + i));  // sum_into_f32
+                    }
+                    xb[i] = x;
+                }
+            }
+            __syncwarp();
+            // normalize_f32 (math.rs:124-150): norm = sqrt(dot(x, x))
+            for (int b = 0; b < nb; ++b) {
+                const float* xb = X + b * xstride;
+                float p = 0.0f;
+                for (int ch = 0; ch < full; ++ch) {
+                    const float v = xb[ch * 32 + c.lane];
+                    p = __fmaf_rn(v, v, p);
+                }
+                c.tile[b * kTileStride + c.lane] = p;
+            }
+            __syncwarp();
+            float norm = 0.0f;
+            if (c.lane < nb) {
+                const float* xb = X + c.lane * xstride;
+                norm = __fsqrt_rn(ordered_dot(c, c.lane, xb, xb, full, dim));
+            }
+            __syncwarp();
+            for (int b = 0; b < nb; ++b) {
+                const float nrm = __shfl_sync(kFullMask, norm, b);
+                float* xb = X + b * xstride;
+                float p = 0.0f;
+                if (nrm > 0.0f)
+                    for (int i = c.lane; i < dim; i += 32) xb[i] = __fdiv_rn(xb[i], nrm);
+                __syncwarp();
+                // angular distance to the query (angular.rs:63-74)
+                for (int ch = 0; ch < full; ++ch) p = __fmaf_rn(xb[ch * 32 + c.lane], c.qs[ch * 32 + c.lane], p);
+                c.tile[b * kTileStride + c.lane] = p;
+            }
+            __syncwarp();
+            float db = 0.0f;
+            if (c.lane < nb) db = finish_angular(ordered_dot(c, c.lane, X + c.lane * xstride, c.qs, full, dim), &c.status);
+            const float dj = __shfl_sync(kFullMask, db, (c.lane - j0) & 31);
+            if (c.lane >= j0 && c.lane < j0 + nb) d = dj;
+        }
+        __syncwarp();
         return d;
     }
 };
@@ -1235,10 +1306,13 @@ __global__ void __launch_bounds__(32, R > 0 ? GB_MIN_BLOCKS : 1) search_kernel(c
     if (ix.kind == kSumEmbeddings) sp += (qbytes + 15u) & ~15u;
     c.stg = nullptr;
     c.stg_rows = a.stg_rows;
-    if (Dist::kStaged) {
+    c.stg_row_bytes = a.stg_row_bytes;
+    if (a.stg_rows) {  // staging tile: bulk-copied candidate rows (f32 / i8) or summed candidate vectors (embeddings)
         sp = smem_raw + (((size_t)(sp - smem_raw) + 127u) & ~(size_t)127u);
         c.stg = sp;
         sp += (size_t)a.stg_rows * a.stg_row_bytes;
+    }
+    if (Dist::kStaged) {
         if (c.lane == 0) mbar_init(c.bar, 1);
         __syncwarp();
     }
