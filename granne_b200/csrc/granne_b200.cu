@@ -358,11 +358,12 @@ template <class Dist, int R>
 int launch_kernels(Handle* h, Workspace* w, gb::SearchArgs a, const LaunchPlan& plan, cudaStream_t stream) {
     auto kern = gb::search_kernel<Dist, R>;
     auto slow = gb::search_kernel<Dist, 0>;
-    static std::atomic<bool> attr_set{false};
-    if (!attr_set.load()) {
+    static std::atomic<bool> attr_set[64];  // function attributes are per device
+    const int dslot = h->device & 63;
+    if (!attr_set[dslot].load()) {
         GB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
         GB_CUDA(cudaFuncSetAttribute(slow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
-        attr_set.store(true);
+        attr_set[dslot].store(true);
     }
     // fast pass
     static std::mutex occ_mu;
