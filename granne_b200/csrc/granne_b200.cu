@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <map>
@@ -380,6 +381,11 @@ int launch_kernels(Handle* h, Workspace* w, gb::SearchArgs a, const LaunchPlan& 
         }
     }
     if (occ < 1) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "max_search too large for the shared-memory workspace");
+    static const int occ_cap = [] {  // tuning/diagnostic knob: cap the resident one-warp CTAs per SM
+        const char* e = std::getenv("GRANNE_B200_MAX_CTAS_PER_SM");
+        return e ? std::max(1, std::atoi(e)) : 1 << 20;
+    }();
+    occ = std::min(occ, occ_cap);
     const unsigned long long slots = (unsigned long long)occ * h->num_sms;
     const unsigned grid = (unsigned)std::min<unsigned long long>(a.nq, slots);
     if (R > 0) {
