@@ -598,22 +598,15 @@ __device__ __forceinline__ void stcg_u4(uint4* p, uint4 v, unsigned long long po
                  : "memory");
 }
 __device__ __forceinline__ bool vis_bucket_insert(uint32_t* tab, uint32_t nbuckets, uint32_t id, bool valid,
-                                                  bool* overflow, unsigned long long policy, bool preloaded = false,
-                                                  uint4 pre_lo = make_uint4(0, 0, 0, 0),
-                                                  uint4 pre_hi = make_uint4(0, 0, 0, 0)) {
+                                                  bool* overflow, unsigned long long policy) {
     uint32_t b = __umulhi(id * 0x9E3779B1u, nbuckets);
     bool pending = valid, is_new = false;
     for (int probe = 0;; ++probe) {
         uint32_t* bucket = tab + (size_t)b * 8u;
         uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
         if (pending) {
-            if (preloaded && probe == 0) {  // the home bucket was read ahead of time (table unchanged since)
-                lo = pre_lo;
-                hi = pre_hi;
-            } else {
-                lo = ldcg_u4(bucket, policy);
-                hi = ldcg_u4(bucket + 4, policy);
-            }
+            lo = ldcg_u4(bucket, policy);
+            hi = ldcg_u4(bucket + 4, policy);
         }
         const bool found = (lo.x == id) | (lo.y == id) | (lo.z == id) | (lo.w == id) | (hi.x == id) |
                            (hi.y == id) | (hi.z == id) | (hi.w == id);
@@ -929,8 +922,6 @@ __device__ __forceinline__ void search_layer_fast(const DeviceIndex& ix, WarpCtx
     }
     uint32_t n = 1, n_exp = 0, cursor = 0, pos_thr = 0, thr_bits = 0;
     uint32_t spec_id = kUnusedId, spec_nb = kUnusedId;
-    uint4 spec_lo = make_uint4(0, 0, 0, 0), spec_hi = spec_lo;  // home visited bucket of spec_nb, read ahead
-    bool spec_buckets = false;
 
     while (true) {
         // ---- pq.pop(): first unexpanded entry at or after the cursor; also find the runner-up ----
@@ -955,14 +946,11 @@ __device__ __forceinline__ void search_layer_fast(const DeviceIndex& ix, WarpCtx
         // so that the load latency overlaps this whole expansion; a wrong guess only costs the load.
         uint32_t cur_nb = kUnusedId;
         const bool have_cur = (spec_id == xid) && (width <= 32u);
-        const bool have_buckets = have_cur && spec_buckets;
-        const uint4 cur_lo = spec_lo, cur_hi = spec_hi;
         if (have_cur) {
             cur_nb = spec_nb;
             c.n_spec += 1;
         }
         spec_id = kUnusedId;
-        spec_buckets = false;
         {
             const unsigned rest = sel_mask & (sel_mask - 1);
             if (rest && width <= 32u) {
@@ -1012,8 +1000,7 @@ __device__ __forceinline__ void search_layer_fast(const DeviceIndex& ix, WarpCtx
             if (vm == 0) break;
             c.n_nbr += __popc(vm);
             bool ovf = false;
-            const bool is_new =
-                vis_bucket_insert(c.visited, nbuckets, nb, valid, &ovf, c.pol_keep, have_buckets, cur_lo, cur_hi);
+            const bool is_new = vis_bucket_insert(c.visited, nbuckets, nb, valid, &ovf, c.pol_keep);
             const unsigned nm = __ballot_sync(kFullMask, is_new);
             const int k = __popc(nm);
             vis_count += k;
@@ -1034,16 +1021,10 @@ __device__ __forceinline__ void search_layer_fast(const DeviceIndex& ix, WarpCtx
                 return;
             }
             const uint32_t my_d = __float_as_uint(d);
-            if (spec_id != kUnusedId && !spec_buckets) {
-                // The speculative row has had a whole distance phase to arrive: read the home visited bucket of each of
-                // its neighbours now.  The table only changes at the start of the NEXT expansion (its own inserts), so
-                // the values stay valid, and the L2 round trip overlaps the merge below.
-                if (spec_nb != kUnusedId) {
-                    const uint32_t pb = __umulhi(spec_nb * 0x9E3779B1u, nbuckets);
-                    spec_lo = ldcg_u4(c.visited + (size_t)pb * 8u, c.pol_keep);
-                    spec_hi = ldcg_u4(c.visited + (size_t)pb * 8u + 4, c.pol_keep);
-                }
-                spec_buckets = true;
+            if (spec_id != kUnusedId && spec_nb != kUnusedId) {
+                // the speculative row has had a whole distance phase to arrive: warm L2 with its visited buckets
+                const uint32_t pb = __umulhi(spec_nb * 0x9E3779B1u, nbuckets);
+                asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(c.visited + (size_t)pb * 8u));
             }
             // !res.is_full() || distance < res.peek().0   (:1029)
             bool pass = (lane < k) && (n_exp < ef || my_d < thr_bits);
