@@ -29,7 +29,7 @@
 #include <stdint.h>
 
 #ifndef GB_MIN_BLOCKS
-#define GB_MIN_BLOCKS 20  // resident one-warp CTAs per SM the fast kernel is register-limited to (tuning knob)
+#define GB_MIN_BLOCKS 24  // resident one-warp CTAs per SM the fast kernel is register-limited to (tuning knob)
 #endif
 #ifndef GB_STG_BYTES
 #define GB_STG_BYTES 4096  // staging tile per warp for bulk-copied candidate rows (tuning knob)
@@ -948,7 +948,6 @@ __device__ __forceinline__ void search_layer_fast(const DeviceIndex& ix, WarpCtx
         const bool have_cur = (spec_id == xid) && (width <= 32u);
         if (have_cur) {
             cur_nb = spec_nb;
-            c.n_spec += 1;
         }
         spec_id = kUnusedId;
         {
@@ -1034,7 +1033,6 @@ __device__ __forceinline__ void search_layer_fast(const DeviceIndex& ix, WarpCtx
             const unsigned pm = __ballot_sync(kFullMask, pass);
             if (pm == 0) continue;
             const uint32_t m = __popc(pm);
-            c.n_ins += m;
 
             // rank of my key among the entries: branch-free lower bound on the distance over the padded array
             // (entries at positions >= n are sentinels), refined by id on exact distance ties
