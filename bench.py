@@ -8,7 +8,7 @@ this bench can BUILD inside its time budget (the 100M x 128 configuration of the
  so that recall@10 >= 0.95 is reachable; recall is measured against an exact brute force and reported.
 
 One step = one batch of 1024 queries per rank through Granne::search semantics (granne_b200_search_batch*).  Steps
-are independent batches; they are issued round-robin on a few CUDA streams (a serving system would do the same), then
+are independent batches; they are issued round-robin on 8 CUDA streams (a serving system would do the same), then
 the whole timed region is bracketed by barrier + synchronize and timed with CUDA events (max over ranks).
   value   device-resident: queries already in HBM, results left in HBM (+ NCCL all-gather of the result tiles, N > 1)
   e2e     host buffers through the public API (granne_b200.Granne.search_batch): H2D of the queries and D2H of the
@@ -49,7 +49,7 @@ def parse_args():
     ap.add_argument("--max-search", type=int, default=200)
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--num-neighbors", type=int, default=30)
-    ap.add_argument("--streams", type=int, default=4)
+    ap.add_argument("--streams", type=int, default=8)
     ap.add_argument("--graphs", type=int, default=0, help="replay each step from a CUDA graph (0 = eager launches)")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: p2p = kernels store result tiles into every peer's buffer (fused epilogue over "
@@ -440,7 +440,7 @@ def main():
     solo_ms = float(np.median(solo[1:]))
 
     # ---- end to end through the public host API ------------------------------------------------------------------------
-    nthreads = max(1, min(a.streams, 4))
+    nthreads = max(1, min(a.streams, 8))
     h2d = a.nq * a.dim * 4
     d2h = a.nq * a.k * 8 + a.nq * 4
 
