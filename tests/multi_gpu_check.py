@@ -43,7 +43,7 @@ def main():
     assert np.array_equal(d.cpu().numpy().view(np.uint32), ref_d.view(np.uint32)), "replicated dists"
 
     # mode 1 with the fused gather: kernels store their tiles straight into every peer's buffer (no collective)
-    per = 128
+    per = min(128, q.shape[0] // world)  # every rank needs a full slice of the 1000 test queries
     fg = FusedGather(per, 10, slots=2)
     for step in range(3):
         lq = tq[rank * per:(rank + 1) * per]
