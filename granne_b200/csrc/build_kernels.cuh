@@ -197,7 +197,7 @@ __device__ __forceinline__ void setup_ctx(const DeviceIndex& ix, WarpCtx& c, Lin
     }
     c.status = 0;
     c.q_norm_i8 = 0;
-    c.n_dist = c.n_expand = c.n_nbr = c.n_ins = 0;
+    c.n_dist = c.n_expand = c.n_nbr = 0;
     c.list = nullptr;
     c.visited = nullptr;
     s.cid = reinterpret_cast<uint32_t*>(sp);

@@ -184,7 +184,7 @@ struct WarpCtx {
     int lane;
     int status;
     int q_norm_i8;     // ANGULAR_INT: dy = sum q^2
-    uint32_t n_dist, n_expand, n_nbr, n_ins, n_spec;
+    uint32_t n_dist, n_expand, n_nbr;
 };
 
 // ---- mbarrier + 1-D bulk copy (TMA, UBLKCP) helpers ----------------------------------------------------------------
@@ -1347,7 +1347,7 @@ __global__ void __launch_bounds__(32, R > 0 ? GB_MIN_BLOCKS : 1) search_kernel(c
         if (a.slow_pass && a.query_status[qi] != kStatusOverflow) continue;  // only flagged queries
 
         c.status = 0;
-        c.n_dist = c.n_expand = c.n_nbr = c.n_ins = c.n_spec = 0;
+        c.n_dist = c.n_expand = c.n_nbr = 0;
         c.q_norm_i8 = 0;
         prepare_query(ix, a, c, qi);
         dist.load_query(ix, c);
@@ -1451,8 +1451,7 @@ __global__ void __launch_bounds__(32, R > 0 ? GB_MIN_BLOCKS : 1) search_kernel(c
                 a.out_stats[qi * 4 + 0] = c.n_dist;
                 a.out_stats[qi * 4 + 1] = c.n_expand;
                 a.out_stats[qi * 4 + 2] = c.n_nbr;
-                a.out_stats[qi * 4 + 3] = (a.slow_pass ? 1ull : 0ull) | ((unsigned long long)(c.n_ins & 0xFFFFFFu) << 8) |
-                                          ((unsigned long long)c.n_spec << 32);
+                a.out_stats[qi * 4 + 3] = a.slow_pass ? 1ull : 0ull;
             }
             if (!(c.status & kStatusOverflow)) a.query_status[qi] = 0;
         }

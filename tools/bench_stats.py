@@ -14,6 +14,6 @@ tq = torch.from_numpy(clustered(4096, 128, 4321, nc)).cuda()
 stats = torch.zeros((4096, 4), dtype=torch.int64, device="cuda")
 p.search_batch_device(tq, 200, 10, stats=stats); torch.cuda.synchronize(); p.stream_status()
 st = stats.cpu().numpy()
-print("n_dist %.0f n_expand %.0f (max %d) n_nbr %.0f inserts %.0f spec_hits %.0f slow %d" % (st[:,0].mean(), st[:,1].mean(), st[:,1].max(), st[:,2].mean(), ((st[:,3]>>8)&0xFFFFFF).mean(), (st[:,3]>>32).mean(), (st[:,3]&1).sum()))
+print("n_dist %.0f n_expand %.0f (max %d) n_nbr %.0f slow %d" % (st[:,0].mean(), st[:,1].mean(), st[:,1].max(), st[:,2].mean(), (st[:,3]&1).sum()))
 degs = [len(p.get_neighbors(i)) for i in range(0, n, n // 2000)]
 print("bottom degree mean %.1f min %d max %d" % (np.mean(degs), min(degs), max(degs)))
