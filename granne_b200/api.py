@@ -59,6 +59,7 @@ def load_library():
         "granne_b200_merge_topk_device": (i32, [i32, vp, vp, vp, sz, sz, u32, vp, vp, vp]),
         "granne_b200_inspect_index": (i32, [vp, sz, vp, vp, vp, vp, sz]),
         "granne_b200_decode_layer": (i32, [vp, sz, u64, vp, sz]),
+        "granne_b200_reencode_index": (i32, [vp, sz, vp, sz, C.POINTER(sz)]),
         "granne_b200_build_config_default": (None, [vp]),
         "granne_b200_builder_new": (i32, [vp, i32, vp, sz, vp, sz, i32, C.POINTER(vp)]),
         "granne_b200_builder_build": (i32, [vp, u64]),
@@ -377,6 +378,17 @@ def inspect_index(index_bytes):
     widths = np.zeros(64, dtype=np.uint32)
     _check(L.granne_b200_inspect_index(_ptr(ib), ib.size, C.byref(nl), _ptr(lens), _ptr(degs), _ptr(widths), 64))
     return [(int(lens[i]), int(degs[i]), int(widths[i])) for i in range(nl.value)]
+
+
+def reencode_index(index_bytes):
+    """Host-only: decode an index image and write it again with the library's writer (Index::write_index)."""
+    L = load_library()
+    ib = np.frombuffer(index_bytes, dtype=np.uint8)
+    need = C.c_size_t()
+    _check(L.granne_b200_reencode_index(_ptr(ib), ib.size, None, 0, C.byref(need)))
+    out = np.empty(need.value, dtype=np.uint8)
+    _check(L.granne_b200_reencode_index(_ptr(ib), ib.size, _ptr(out), out.size, C.byref(need)))
+    return out.tobytes()
 
 
 def decode_layer(index_bytes, layer):

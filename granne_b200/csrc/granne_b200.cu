@@ -1275,6 +1275,27 @@ int granne_b200_elements_from_raw(int element_kind, const float* raw, uint64_t n
     return rc;
 }
 
+int granne_b200_reencode_index(const void* index_bytes, size_t index_len, void* out, size_t cap, size_t* out_len) {
+    if (!index_bytes || !out_len) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "null argument");
+    try {
+        gb::HostGraph graph;
+        std::string err;
+        if (!gb::parse_index(static_cast<const uint8_t*>(index_bytes), index_len, &graph, &err))
+            return fail(GRANNE_B200_ERR_FORMAT, err);
+        std::vector<gb::LayerView> views;
+        for (const gb::HostLayer& L : graph.layers) views.push_back({L.rows.data(), L.num_nodes, L.width});
+        std::vector<uint8_t> image;
+        if (!gb::encode_index(views, &image, &err)) return fail(GRANNE_B200_ERR_FORMAT, err);
+        *out_len = image.size();
+        if (!out) return GRANNE_B200_OK;
+        if (cap < image.size()) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "output buffer too small");
+        std::memcpy(out, image.data(), image.size());
+        return GRANNE_B200_OK;
+    } catch (const std::exception& e) {
+        return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, std::string("exception: ") + e.what());
+    }
+}
+
 int granne_b200_merge_topk_device(int device, const uint32_t* d_part_ids, const float* d_part_dists,
                                   const uint64_t* part_base, size_t num_parts, size_t nq, uint32_t k,
                                   uint64_t* d_out_ids, float* d_out_dists, void* cuda_stream) {

@@ -230,6 +230,11 @@ void granne_b200_builder_free(granne_b200_builder* b);
 int granne_b200_elements_from_raw(int element_kind, const float* raw, uint64_t n, uint32_t dim, int device, void* out,
                                   size_t cap, size_t* out_len);
 
+/* Host-only: decodes an index image and writes it again with this library's writer (Index::write_index,
+ * src/index/io.rs:11-70).  For an image written by granne (sorted lists, same coding rules) the output is byte-identical
+ * to the input; used to test the writer without a device.  Call with out == NULL to query the size. */
+int granne_b200_reencode_index(const void* index_bytes, size_t index_len, void* out, size_t cap, size_t* out_len);
+
 /* Number of kernels this library launched on behalf of `h` since it was opened (bench.py's gpu_launches). */
 uint64_t granne_b200_launch_count(const granne_b200_index* h);
 

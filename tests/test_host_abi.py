@@ -122,3 +122,19 @@ def test_open_without_a_gpu_fails_loudly(lib, oracle):
     assert ei.value.code == -5  # GRANNE_B200_ERR_NO_DEVICE: no CPU fallback
     with pytest.raises(ValueError):
         granne_b200.Granne.from_bytes(index_bytes, "bogus", elements_bytes)
+
+
+@pytest.mark.parametrize("n,dim,m", [(1, 8, 5), (60, 8, 5), (61, 8, 5), (1500, 16, 20), (4000, 8, 30)])
+def test_writer_is_byte_identical_to_the_oracle_writer(lib, oracle, n, dim, m):
+    # Index::write_index (src/index/io.rs:11-70, set_vector.rs:117-148,169-221, offsets.rs:233-241): the product's
+    # writer re-encodes an oracle-written image byte for byte (header JSON, offset chunks, raw-vs-vbyte rule)
+    el, g, index_bytes, _, _ = build_fixture(oracle, "angular", n, dim, seed=n + 1, num_neighbors=m, max_search=30)
+    assert api.reencode_index(index_bytes) == index_bytes
+
+
+def test_writer_round_trips_the_golden_images(lib):
+    import glob
+
+    for path in glob.glob(os.path.join(ROOT, "tests", "golden", "*.npz")):
+        image = np.load(path)["index"].tobytes()
+        assert api.reencode_index(image) == image
