@@ -66,6 +66,8 @@ def load_library():
         "granne_b200_builder_len": (u64, [vp]),
         "granne_b200_builder_num_layers": (u64, [vp]),
         "granne_b200_builder_layer_len": (u64, [vp, u64]),
+        "granne_b200_builder_num_elements": (u64, [vp]),
+        "granne_b200_builder_get_neighbors": (i32, [vp, u64, u64, vp, sz, C.POINTER(sz)]),
         "granne_b200_builder_write_index": (i32, [vp, vp, sz, C.POINTER(sz)]),
         "granne_b200_builder_get_index": (i32, [vp, C.POINTER(vp)]),
         "granne_b200_builder_free": (None, [vp]),
@@ -118,6 +120,8 @@ class Granne:
                                         C.byref(h)))
         self._h = h
         self.device = device
+        self._index_src = ("path", index_path)
+        self._elements_src = ("path", elements_path)
 
     @classmethod
     def from_bytes(cls, index_bytes, element_type, elements_bytes, embeddings_bytes=None, device=0):
@@ -133,7 +137,32 @@ class Granne:
                                   C.byref(h)))
         self._h = h
         self.device = device
+        self._index_src = ("bytes", index_bytes)
+        self._elements_src = ("bytes", elements_bytes)
         return self
+
+    @staticmethod
+    def _source_bytes(src):
+        if src is None:
+            raise GranneError(-1, "this handle does not own a host image of that data")
+        kind, value = src
+        if kind == "path":
+            with open(value, "rb") as f:
+                return f.read()
+        if kind == "call":
+            return value()
+        return bytes(value)
+
+    def save_index(self, path):
+        """Granne.save_index(path) (py/src/lib.rs:325-329): Index::write_index of the loaded graph."""
+        with open(path, "wb") as f:
+            f.write(reencode_index(self._source_bytes(getattr(self, "_index_src", None))))
+
+    def save_elements(self, path):
+        """Granne.save_elements(path) (py/src/lib.rs:339-343): the elements file (u64 dim + rows,
+        src/slice_vector/mod.rs:460-466; offsets + 3-byte ids for "embeddings")."""
+        with open(path, "wb") as f:
+            f.write(self._source_bytes(getattr(self, "_elements_src", None)))
 
     def close(self):
         if getattr(self, "_h", None):
@@ -319,6 +348,7 @@ class GranneBuilder:
                                          device, C.byref(h)))
         self._h = h
         self.device = device
+        self._elements_bytes = elements_bytes
 
     def build(self, num_elements=0):
         """Builder::build() / build_partial(num_elements)."""
@@ -354,7 +384,29 @@ class GranneBuilder:
         g = Granne.__new__(Granne)
         g._h = h
         g.device = self.device
+        image = self.index_bytes().tobytes()  # snapshot: later build() calls do not change this Granne
+        g._index_src = ("bytes", image)
+        g._elements_src = ("bytes", self._elements_bytes)
         return g
+
+    def save_elements(self, path):
+        """GranneBuilder.save_elements(path) (py/src/lib.rs:518-522)."""
+        with open(path, "wb") as f:
+            f.write(bytes(self._elements_bytes))
+
+    def get_neighbors(self, idx, layer=None):
+        """GranneBuilder.get_neighbors(idx, layer=last) (py/src/lib.rs:544-552)."""
+        if layer is None:
+            layer = self.num_layers() - 1
+        out = np.empty(256, dtype=np.uint32)
+        n = C.c_size_t()
+        _check(load_library().granne_b200_builder_get_neighbors(self._h, idx, layer, _ptr(out), out.size,
+                                                                C.byref(n)))
+        return out[:n.value].tolist()
+
+    def num_elements(self):
+        """GranneBuilder.num_elements() (py/src/lib.rs:559-561): elements held, indexed or not."""
+        return int(load_library().granne_b200_builder_num_elements(self._h))
 
     def close(self):
         if getattr(self, "_h", None):

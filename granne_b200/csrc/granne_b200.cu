@@ -1163,6 +1163,12 @@ uint64_t granne_b200_builder_layer_len(const granne_b200_builder* b, uint64_t la
     if (!b || layer >= (uint64_t)b->h->dev.num_layers) return 0;
     return b->h->dev.layer_len[layer];
 }
+uint64_t granne_b200_builder_num_elements(const granne_b200_builder* b) { return b ? b->h->dev.num_elements : 0; }
+int granne_b200_builder_get_neighbors(const granne_b200_builder* b, uint64_t idx, uint64_t layer, uint32_t* out,
+                                      size_t cap, size_t* n_out) {
+    if (!b) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "null builder");
+    return granne_b200_get_neighbors(b->h.get(), idx, layer, out, cap, n_out);
+}
 
 int granne_b200_builder_write_index(granne_b200_builder* b, void* out, size_t cap, size_t* out_len) {
     if (!b || !out_len) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "null argument");

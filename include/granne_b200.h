@@ -215,6 +215,11 @@ int granne_b200_builder_build(granne_b200_builder* b, uint64_t num_elements);
 uint64_t granne_b200_builder_len(const granne_b200_builder* b);        /* Index::len for the builder (:329-331) */
 uint64_t granne_b200_builder_num_layers(const granne_b200_builder* b); /* :334-336 */
 uint64_t granne_b200_builder_layer_len(const granne_b200_builder* b, uint64_t layer);
+/* Builder::num_elements (src/index/mod.rs:404-406): elements held by the builder, indexed or not. */
+uint64_t granne_b200_builder_num_elements(const granne_b200_builder* b);
+/* Index::get_neighbors for the builder (:339-349); same contract as granne_b200_get_neighbors. */
+int granne_b200_builder_get_neighbors(const granne_b200_builder* b, uint64_t idx, uint64_t layer, uint32_t* out,
+                                      size_t cap, size_t* n_out);
 /* Index::write_index (:358-361, src/index/io.rs:11-70): the granne index file image (compressed layers).  Call with
  * out == NULL to query the size; the image is readable by granne itself and by granne_b200_open. */
 int granne_b200_builder_write_index(granne_b200_builder* b, void* out, size_t cap, size_t* out_len);

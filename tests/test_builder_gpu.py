@@ -138,3 +138,38 @@ def test_builder_queries_that_overflow_the_fast_path():
     assert _self_recall(index, rows[:3000], 40) > 0.9
     index.close()
     b.close()
+
+
+def test_python_class_surface_save_and_reload(tmp_path, oracle):
+    # py/src/lib.rs:325-343 (Granne.save_index / save_elements), :504-579 (GranneBuilder.save_index / save_elements /
+    # get_neighbors / num_elements): the files written are granne files — the oracle's loader reads them back
+    raw = random_vectors(900, 16, seed=21)
+    eb = granne_b200.elements_from_raw("angular", raw).tobytes()
+    b = granne_b200.GranneBuilder("angular", eb, num_neighbors=12, max_search=30)
+    b.build(500)
+    assert len(b) == 500 and b.num_elements() == 900
+    b.build()
+    ip, ep = str(tmp_path / "index.granne"), str(tmp_path / "elements.bin")
+    b.save_index(ip)
+    b.save_elements(ep)
+    index = granne_b200.Granne(ip, "angular", ep)
+    assert len(index) == 900 and index.num_elements() == 900
+    last = index.num_layers() - 1
+    for node in (0, 1, 17, 899):
+        # builder rows are in insertion order (FixedWidthSliceVector), file rows are sorted (set_vector.rs:117-148)
+        assert sorted(b.get_neighbors(node)) == index.get_neighbors(node) == index.get_neighbors(node, last)
+    assert sorted(b.get_neighbors(0, 0)) == index.get_neighbors(0, 0)
+    ip2, ep2 = str(tmp_path / "index2.granne"), str(tmp_path / "elements2.bin")
+    index.save_index(ip2)
+    index.save_elements(ep2)
+    assert open(ip2, "rb").read() == open(ip, "rb").read() and open(ep2, "rb").read() == eb
+    snap = b.get_index()
+    snap.save_index(ip2)
+    assert open(ip2, "rb").read() == open(ip, "rb").read()
+    ref = oracle.Granne.from_bytes(open(ip, "rb").read(), oracle.Elements.from_bytes("angular", open(ep, "rb").read()))
+    q = random_vectors(64, 16, seed=22)
+    want = ref.search_batch(q, 30, 5)
+    got = index.search_batch(q, 30, 5)
+    assert np.array_equal(want[0], got[0]) and np.array_equal(want[1].view(np.uint32), got[1].view(np.uint32))
+    for h in (snap, index, b):
+        h.close()
