@@ -19,6 +19,7 @@
 // Build: g++ -O3 -std=c++17 -mavx2 -mfma -ffp-contract=off -fPIC -shared -pthread (see oracle/Makefile).
 
 #include <algorithm>
+#include <array>
 #include <atomic>
 #include <cmath>
 #include <cstdint>
@@ -655,6 +656,159 @@ std::vector<std::pair<u64, float>> index_search(const Index& ix, size_t num_laye
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// reorder (src/index/reorder.rs:59-292, src/slice_vector/mod.rs:437-458, src/elements/embeddings/mod.rs:191-217,
+// src/elements/embeddings/reorder.rs:31-58)
+// ---------------------------------------------------------------------------------------------------------------
+constexpr size_t TRAIL_LAYERS = 8;  // reorder.rs:177
+using Trail = std::array<u32, TRAIL_LAYERS>;
+
+// reorder.rs:180-207 (find_entrypoint_trail): the closest element (max_search = 1) in each of the first
+// min(8, max_layer) layers.  The reference seeds layer i with `eps[i]`, which is still 0 at that point, so every layer
+// is searched from node 0 (not from the previous layer's result); this restatement keeps that behaviour.
+Trail find_entrypoint_trail(const Index& ix, const Elements& el, size_t max_layer, const Query& q) {
+    Trail eps{};
+    const size_t take = std::min<size_t>(std::min(TRAIL_LAYERS, max_layer), ix.num_layers());
+    for (size_t i = 0; i < take; ++i) {
+        const u64 ep = (i == 0) ? 0 : eps[i];
+        auto res = search_for_neighbors([&](size_t n, std::vector<u32>& o) { ix.get_neighbors(i, n, o); }, ep, el, q,
+                                        1, nullptr);
+        eps[i] = (u32)res[0].first;
+    }
+    return eps;
+}
+
+// reorder.rs:126-174 (compute_order).  `order_inv` is only filled for ids >= layer_len(0) (reorder.rs:161-165); ids of
+// the first layer map to 0, as in the reference.  (trail, idx) tuples are unique, so the unstable sort is deterministic.
+std::vector<u64> compute_order(const Index& ix, const Elements& el, int threads) {
+    const size_t nl = ix.num_layers();
+    std::vector<u64> order;
+    if (nl == 0) return order;
+    for (size_t i = 0; i < ix.layer_len(0); ++i) order.push_back(i);
+    std::vector<u64> order_inv(nl >= 2 ? ix.layer_len(nl - 2) : 0, 0);
+    for (size_t layer = 1; layer < nl; ++layer) {
+        const size_t begin = ix.layer_len(layer - 1), end = ix.layer_len(layer);
+        std::vector<std::pair<Trail, u64>> eps(end - begin);
+        auto run = [&](size_t b, size_t e) {
+            Query q;
+            for (size_t idx = b; idx < e; ++idx) {
+                el.get(idx, &q);
+                Trail t = find_entrypoint_trail(ix, el, layer, q);
+                for (auto& v : t) v = (u32)order_inv[v];
+                eps[idx - begin] = {t, idx};
+            }
+        };
+        if (threads <= 1 || end - begin < 64) {
+            run(begin, end);
+        } else {
+            std::vector<std::thread> ts;
+            const size_t per = (end - begin + threads - 1) / threads;
+            for (int t = 0; t < threads; ++t) {
+                const size_t b = std::min(end, begin + per * t), e = std::min(end, begin + per * (t + 1));
+                if (b < e) ts.emplace_back(run, b, e);
+            }
+            for (auto& t : ts) t.join();
+        }
+        std::sort(eps.begin(), eps.end());
+        for (auto& e : eps) order.push_back(e.second);
+        if (layer < nl - 1)
+            for (size_t i = begin; i < end; ++i) order_inv[order[i]] = i;
+    }
+    return order;
+}
+
+// reorder.rs:89-124 (reorder_by_keys, the ordering part): a layer-preserving sort by (key, idx); keys are rows of
+// `kw` u64 compared lexicographically (covers integer keys and the [usize; 8] keys of compute_keys_for_reordering).
+std::vector<u64> order_by_keys(const Index& ix, const u64* keys, size_t kw) {
+    std::vector<u64> order;
+    for (size_t layer = 0; layer < ix.num_layers(); ++layer) {
+        const size_t begin = layer ? ix.layer_len(layer - 1) : 0, end = ix.layer_len(layer);
+        std::vector<u64> ids;
+        for (size_t i = begin; i < end; ++i) ids.push_back(i);
+        std::sort(ids.begin(), ids.end(), [&](u64 a, u64 b) {
+            for (size_t j = 0; j < kw; ++j)
+                if (keys[a * kw + j] != keys[b * kw + j]) return keys[a * kw + j] < keys[b * kw + j];
+            return a < b;
+        });
+        order.insert(order.end(), ids.begin(), ids.end());
+    }
+    return order;
+}
+
+// reorder.rs:209-292 (reorder_layers / reorder_layer / get_reverse_mapping): node i of the new layer gets the
+// neighbours of old node mapping[i], renamed through the reverse mapping; MultiSetVector::push sorts each list
+// (set_vector.rs:41-47).  The result is returned as fixed-width rows (sorted), ready for write_index_bytes.
+void reorder_layers(const Index& ix, const std::vector<u64>& mapping, Index* out) {
+    std::vector<u64> rev(mapping.size(), 0);
+    for (size_t i = 0; i < mapping.size(); ++i) rev[mapping[i]] = i;
+    std::vector<std::vector<std::vector<u32>>> lists(ix.num_layers());
+    size_t w = 1;
+    std::vector<u32> tmp;
+    for (size_t l = 0; l < ix.num_layers(); ++l) {
+        lists[l].resize(ix.layer_len(l));
+        for (size_t i = 0; i < ix.layer_len(l); ++i) {
+            ix.get_neighbors(l, (size_t)mapping[i], tmp);
+            for (u32& n : tmp) n = (u32)rev[n];
+            std::sort(tmp.begin(), tmp.end());
+            w = std::max(w, tmp.size());
+            lists[l][i] = tmp;
+        }
+    }
+    out->use_fixed = true;
+    out->width = w;
+    out->fixed.clear();
+    for (size_t l = 0; l < ix.num_layers(); ++l) {
+        std::vector<u32> rows(lists[l].size() * w, UNUSED);
+        for (size_t i = 0; i < lists[l].size(); ++i) std::copy(lists[l][i].begin(), lists[l][i].end(), rows.begin() + i * w);
+        out->fixed.push_back(std::move(rows));
+    }
+}
+
+// Permutable::permute — FixedWidthSliceVector (slice_vector/mod.rs:437-458) and SumEmbeddings
+// (embeddings/mod.rs:191-217): new element i = old element permutation[i].
+void permute_elements(Elements* el, const std::vector<u64>& perm) {
+    const size_t n = el->n, dim = el->dim;
+    if (el->kind == KIND_F32) {
+        std::vector<float> r(el->f32.size());
+        for (size_t i = 0; i < n; ++i) std::memcpy(&r[i * dim], &el->f32[(size_t)perm[i] * dim], dim * sizeof(float));
+        el->f32.swap(r);
+    } else if (el->kind == KIND_I8) {
+        std::vector<int8_t> r(el->i8.size());
+        for (size_t i = 0; i < n; ++i) std::memcpy(&r[i * dim], &el->i8[(size_t)perm[i] * dim], dim);
+        el->i8.swap(r);
+    } else {
+        std::vector<u64> off(1, 0);
+        std::vector<u32> terms;
+        for (size_t i = 0; i < n; ++i) {
+            for (u64 t = el->offsets[perm[i]]; t < el->offsets[perm[i] + 1]; ++t) terms.push_back(el->terms[t]);
+            off.push_back(terms.size());
+        }
+        el->offsets.swap(off);
+        el->terms.swap(terms);
+    }
+}
+
+// embeddings/reorder.rs:31-58 (compute_keys_for_reordering): per element, its embedding ids ordered by decreasing
+// norm (stable sort by norm, then reversed), first 8, zero padded.  The norm is a plain left-to-right f32 sum of
+// squares (`iter().map(|x| x * x).sum::<f32>().sqrt()`), not the 32-lane dot product.
+void embedding_reorder_keys(const Elements& el, u64* keys) {
+    std::vector<float> norms(el.num_embeddings);
+    for (size_t w = 0; w < el.num_embeddings; ++w) {
+        float acc = 0.0f;
+        for (size_t j = 0; j < el.dim; ++j) {
+            const float x = el.f32[w * el.dim + j];
+            acc = acc + x * x;
+        }
+        norms[w] = std::sqrt(acc);
+    }
+    for (size_t q = 0; q < el.n; ++q) {
+        std::vector<u32> ids(el.terms.begin() + el.offsets[q], el.terms.begin() + el.offsets[q + 1]);
+        std::stable_sort(ids.begin(), ids.end(), [&](u32 a, u32 b) { return norms[a] < norms[b]; });
+        std::reverse(ids.begin(), ids.end());
+        for (size_t j = 0; j < TRAIL_LAYERS; ++j) keys[q * TRAIL_LAYERS + j] = j < ids.size() ? ids[j] : 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // builder (src/index/mod.rs:198-231, 366-402, 634-960) — fixture generator.
 // threads == 1 restates the `singlethreaded` feature order (:771-772,789-790); threads > 1 mirrors the rayon
 // par_iter build (:773-774) with per-node locks (nondeterministic, like the reference).
@@ -980,6 +1134,14 @@ void orc_sum_push_element(void* p, const uint32_t* ids, uint64_t n) {
     e->n += 1;
 }
 // raw row access
+uint64_t orc_sum_num_embeddings(void* p) { return ((Elements*)p)->num_embeddings; }
+// SumEmbeddings::get_terms (embeddings/mod.rs:106-108)
+uint64_t orc_sum_terms(void* p, uint64_t idx, uint32_t* out, uint64_t cap) {
+    auto* e = (Elements*)p;
+    const u64 b = e->offsets[idx], n = e->offsets[idx + 1] - b;
+    for (u64 i = 0; i < n && i < cap; ++i) out[i] = e->terms[b + i];
+    return n;
+}
 const void* orc_elements_data(void* p) {
     auto* e = (Elements*)p;
     return e->kind == KIND_I8 ? (const void*)e->i8.data() : (const void*)e->f32.data();
@@ -1204,5 +1366,34 @@ int orc_search_batch(void* index, void* elements, const float* queries, const in
     }
     return 0;
 }
+
+// ---- reorder ----
+void orc_entrypoint_trail(void* index, void* elements, uint64_t idx, uint64_t max_layer, uint32_t* out8) {
+    auto* el = (Elements*)elements;
+    Query q;
+    el->get(idx, &q);
+    Trail t = find_entrypoint_trail(*(Index*)index, *el, max_layer, q);
+    for (size_t i = 0; i < TRAIL_LAYERS; ++i) out8[i] = t[i];
+}
+void orc_compute_order(void* index, void* elements, uint64_t* order_out, int threads) {
+    auto o = compute_order(*(Index*)index, *(Elements*)elements, threads);
+    std::copy(o.begin(), o.end(), order_out);
+}
+void orc_order_by_keys(void* index, const uint64_t* keys, uint64_t kw, uint64_t* order_out) {
+    auto o = order_by_keys(*(Index*)index, keys, kw);
+    std::copy(o.begin(), o.end(), order_out);
+}
+// Returns a new index (compressed, as the reference's reordered Granne holds it) = reorder_layers(index, order).
+void* orc_index_apply_order(void* index, const uint64_t* order, uint64_t n) {
+    Index fixed;
+    reorder_layers(*(Index*)index, std::vector<u64>(order, order + n), &fixed);
+    std::vector<u8> bytes;
+    write_index_bytes(fixed, bytes);
+    return orc_index_from_bytes(bytes.data(), bytes.size());
+}
+void orc_elements_permute(void* elements, const uint64_t* order, uint64_t n) {
+    permute_elements((Elements*)elements, std::vector<u64>(order, order + n));
+}
+void orc_sum_reorder_keys(void* elements, uint64_t* keys_out) { embedding_reorder_keys(*(Elements*)elements, keys_out); }
 
 }  // extern "C"

@@ -62,6 +62,8 @@ def lib():
         "orc_sum_push_embeddings": (None, [vp, vp, u64]),
         "orc_sum_push_element": (None, [vp, vp, u64]),
         "orc_elements_data": (vp, [vp]),
+        "orc_sum_num_embeddings": (u64, [vp]),
+        "orc_sum_terms": (u64, [vp, u64, vp, u64]),
         "orc_elements_get": (None, [vp, u64, vp]),
         "orc_elements_dist_to": (f32, [vp, u64, vp, i32]),
         "orc_elements_serialize": (u64, [vp, i32, vp, u64]),
@@ -75,6 +77,12 @@ def lib():
         "orc_index_num_layers": (u64, [vp]),
         "orc_index_layer_len": (u64, [vp, u64]),
         "orc_index_get_neighbors": (u64, [vp, u64, u64, vp, u64]),
+        "orc_entrypoint_trail": (None, [vp, vp, u64, u64, vp]),
+        "orc_compute_order": (None, [vp, vp, vp, i32]),
+        "orc_order_by_keys": (None, [vp, vp, u64, vp]),
+        "orc_index_apply_order": (vp, [vp, vp, u64]),
+        "orc_elements_permute": (None, [vp, vp, u64]),
+        "orc_sum_reorder_keys": (None, [vp, vp]),
         "orc_search_batch": (i32, [vp, vp, vp, vp, u64, i32, u64, u64, vp, vp, vp, vp, i32]),
     }
     for name, (res, args) in sig.items():
@@ -245,7 +253,7 @@ class Elements:
 
     def rows(self):
         """The stored rows (f32/i8 vectors, or the embedding table for SumEmbeddings) as a numpy copy."""
-        n = len(self)
+        n = int(lib().orc_sum_num_embeddings(self._h)) if self.kind == EMBEDDINGS else len(self)
         p = lib().orc_elements_data(self._h)
         if self.kind == ANGULAR_INT:
             return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_int8)), shape=(n, self.dim)).copy()
@@ -254,6 +262,25 @@ class Elements:
     def dist_to_element(self, idx, raw_query, already_element=False):
         q = _f32(raw_query)
         return np.float32(lib().orc_elements_dist_to(self._h, idx, _ptr(q), int(already_element)))
+
+    def terms(self, idx):
+        """SumEmbeddings::get_terms (embeddings/mod.rs:106-108)."""
+        out = np.zeros(256, dtype=np.uint32)
+        n = int(lib().orc_sum_terms(self._h, idx, _ptr(out), out.size))
+        return out[:n].tolist()
+
+    def permute(self, permutation):
+        """Permutable::permute (slice_vector/mod.rs:437-458, embeddings/mod.rs:191-217): new i = old permutation[i]."""
+        perm = np.ascontiguousarray(permutation, dtype=np.uint64)
+        assert perm.size == len(self)
+        lib().orc_elements_permute(self._h, _ptr(perm), perm.size)
+
+    def reorder_keys(self):
+        """embeddings::compute_keys_for_reordering (embeddings/reorder.rs:31-58) -> uint64 [n, 8]."""
+        assert self.kind == EMBEDDINGS
+        keys = np.zeros((len(self), 8), dtype=np.uint64)
+        lib().orc_sum_reorder_keys(self._h, _ptr(keys))
+        return keys
 
     def to_bytes(self, which=0):
         """io::Writeable::write.  which=1: the SumEmbeddings embeddings table."""
@@ -313,6 +340,42 @@ class Granne:
         out = np.empty(n, dtype=np.uint8)
         lib().orc_index_serialize(self._h, _ptr(out), n)
         return out.tobytes()
+
+    # ---- reorder (src/index/reorder.rs) ----
+    def entrypoint_trail(self, idx, max_layer):
+        """find_entrypoint_trail (reorder.rs:180-207) for element idx."""
+        out = np.zeros(8, dtype=np.uint32)
+        lib().orc_entrypoint_trail(self._h, self.elements._h, idx, max_layer, _ptr(out))
+        return out
+
+    def compute_order(self, threads=1):
+        """Granne::compute_order (reorder.rs:126-174)."""
+        order = np.zeros(len(self), dtype=np.uint64)
+        lib().orc_compute_order(self._h, self.elements._h, _ptr(order), threads)
+        return order
+
+    def order_by_keys(self, keys):
+        """The ordering part of Granne::reorder_by_keys (reorder.rs:96-108); keys uint64 [n] or [n, kw]."""
+        keys = np.ascontiguousarray(keys, dtype=np.uint64).reshape(len(self), -1)
+        order = np.zeros(len(self), dtype=np.uint64)
+        lib().orc_order_by_keys(self._h, _ptr(keys), keys.shape[1], _ptr(order))
+        return order
+
+    def _apply(self, order):
+        order = np.ascontiguousarray(order, dtype=np.uint64)
+        new = lib().orc_index_apply_order(self._h, _ptr(order), order.size)
+        lib().orc_index_free(self._h)
+        self._h = new
+        self.elements.permute(order)
+        return order
+
+    def reorder(self, threads=1):
+        """Granne::reorder (reorder.rs:59-82): reorders this index AND its elements in place; returns the order."""
+        return self._apply(self.compute_order(threads))
+
+    def reorder_by_keys(self, keys):
+        """Granne::reorder_by_keys (reorder.rs:89-124)."""
+        return self._apply(self.order_by_keys(keys))
 
     def search_batch(self, queries, max_search=200, num_neighbors=10, already_element=False, threads=1,
                      with_stats=False):

@@ -48,3 +48,35 @@ def build_fixture(go, kind, n, dim, seed, num_neighbors, max_search, threads=1, 
     # search through the from_bytes path (compressed layers), like a user of the reference would
     g2 = go.Granne.from_bytes(index_bytes, el)
     return el, g2, index_bytes, elements_bytes, emb_bytes
+
+
+def index_from_lists(oracle, layers):
+    """Writes an index file from explicit adjacency lists (oracle writer, src/index/io.rs:11-70)."""
+    import json
+
+    blobs = []
+    for lists in layers:
+        enc = [oracle.set_encode(sorted(l)) for l in lists]
+        offsets = [0]
+        for e in enc:
+            offsets.append(offsets[-1] + len(e))
+        nchunks = 1 + len(lists) // 60
+        chunks = bytearray()
+        for c in range(nchunks):
+            offs = offsets[c * 60:(c + 1) * 60]
+            initial = offs[0] if offs else 0
+            chunks += int(initial).to_bytes(8, "little")
+            prev = initial
+            for i in range(60):
+                if i < len(offs):
+                    chunks += int(offs[i] - prev).to_bytes(2, "little")
+                    prev = offs[i]
+                else:
+                    chunks += b"\xff\xff"
+        blobs.append(len(chunks).to_bytes(8, "little") + bytes(chunks) + b"".join(enc))
+    meta = "granne" + json.dumps({"compressed": True, "granne_version": "0.5.2",
+                                  "layer_counts": [len(l) for l in layers], "layer_sizes": [len(b) for b in blobs],
+                                  "num_elements": len(layers[-1]) if layers else 0, "num_layers": len(layers),
+                                  "num_neighbors": len(layers[-1][0]) if layers else 0, "version": 2},
+                                 separators=(",", ":"))
+    return meta.encode().ljust(1024, b" ") + b"".join(blobs)

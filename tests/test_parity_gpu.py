@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 import granne_b200
-from helpers.data import build_fixture, random_vectors
+from helpers.data import build_fixture, index_from_lists, random_vectors
 
 pytestmark = pytest.mark.gpu
 
@@ -196,7 +196,7 @@ def test_all_identical_vectors_take_the_exact_slow_path(oracle):
     raw = np.tile(random_vectors(1, dim, seed=5), (n, 1))
     el = oracle.Elements.angular(raw)
     nb = [sorted({(i * 30 + j) % n for j in range(1, 31)} - {i}) for i in range(n)]  # disjoint fan-outs
-    ib = _index_from_lists(oracle, [nb])  # written in granne's format through the oracle's list encoder
+    ib = index_from_lists(oracle, [nb])  # written in granne's format through the oracle's list encoder
     g = oracle.Granne.from_bytes(ib, el)
     p = open_product(ib, "angular", el.to_bytes())
     q = random_vectors(8, dim, seed=6)
@@ -210,42 +210,10 @@ def test_all_identical_vectors_take_the_exact_slow_path(oracle):
     p.close()
 
 
-def _index_from_lists(oracle, layers):
-    """Writes an index file from explicit adjacency lists (oracle writer, src/index/io.rs:11-70)."""
-    import json
-
-    blobs = []
-    for lists in layers:
-        enc = [oracle.set_encode(sorted(l)) for l in lists]
-        offsets = [0]
-        for e in enc:
-            offsets.append(offsets[-1] + len(e))
-        nchunks = 1 + len(lists) // 60
-        chunks = bytearray()
-        for c in range(nchunks):
-            offs = offsets[c * 60:(c + 1) * 60]
-            initial = offs[0] if offs else 0
-            chunks += int(initial).to_bytes(8, "little")
-            prev = initial
-            for i in range(60):
-                if i < len(offs):
-                    chunks += int(offs[i] - prev).to_bytes(2, "little")
-                    prev = offs[i]
-                else:
-                    chunks += b"\xff\xff"
-        blobs.append(len(chunks).to_bytes(8, "little") + bytes(chunks) + b"".join(enc))
-    meta = "granne" + json.dumps({"compressed": True, "granne_version": "0.5.2",
-                                  "layer_counts": [len(l) for l in layers], "layer_sizes": [len(b) for b in blobs],
-                                  "num_elements": len(layers[-1]) if layers else 0, "num_layers": len(layers),
-                                  "num_neighbors": len(layers[-1][0]) if layers else 0, "version": 2},
-                                 separators=(",", ":"))
-    return meta.encode().ljust(1024, b" ") + b"".join(blobs)
-
-
 # ---- edge cases ----------------------------------------------------------------------------------------------------
 def test_empty_index_and_single_element(oracle):
     el = oracle.Elements.angular(random_vectors(5, 8, seed=1))
-    ib = _index_from_lists(oracle, [])  # no layers -> search returns Vec::new() (src/index/mod.rs:978-980)
+    ib = index_from_lists(oracle, [])  # no layers -> search returns Vec::new() (src/index/mod.rs:978-980)
     p = open_product(ib, "angular", el.to_bytes())
     ids, dists, counts = p.search_batch(random_vectors(3, 8, seed=2), 10, 4)
     assert (counts == 0).all() and (ids == 0xFFFFFFFF).all() and np.isinf(dists).all()
