@@ -60,6 +60,11 @@ def load_library():
         "granne_b200_inspect_index": (i32, [vp, sz, vp, vp, vp, vp, sz]),
         "granne_b200_decode_layer": (i32, [vp, sz, u64, vp, sz]),
         "granne_b200_reencode_index": (i32, [vp, sz, vp, sz, C.POINTER(sz)]),
+        "granne_b200_compute_order": (i32, [vp, vp, u64]),
+        "granne_b200_order_from_trails": (i32, [vp, u32, vp, u64, vp]),
+        "granne_b200_order_by_keys": (i32, [vp, sz, vp, u64, u32, vp]),
+        "granne_b200_embedding_reorder_keys": (i32, [vp, sz, vp, sz, vp]),
+        "granne_b200_apply_order": (i32, [vp, sz, i32, vp, sz, vp, u64, vp, sz, C.POINTER(sz), vp, sz, C.POINTER(sz)]),
         "granne_b200_build_config_default": (None, [vp]),
         "granne_b200_builder_new": (i32, [vp, i32, vp, sz, vp, sz, i32, C.POINTER(vp)]),
         "granne_b200_builder_build": (i32, [vp, u64]),
@@ -122,6 +127,7 @@ class Granne:
         self.device = device
         self._index_src = ("path", index_path)
         self._elements_src = ("path", elements_path)
+        self._embeddings_src = ("path", embeddings_path) if embeddings_path else None
 
     @classmethod
     def from_bytes(cls, index_bytes, element_type, elements_bytes, embeddings_bytes=None, device=0):
@@ -139,6 +145,7 @@ class Granne:
         self.device = device
         self._index_src = ("bytes", index_bytes)
         self._elements_src = ("bytes", elements_bytes)
+        self._embeddings_src = ("bytes", embeddings_bytes) if embeddings_bytes is not None else None
         return self
 
     @staticmethod
@@ -163,6 +170,35 @@ class Granne:
         src/slice_vector/mod.rs:460-466; offsets + 3-byte ids for "embeddings")."""
         with open(path, "wb") as f:
             f.write(self._source_bytes(getattr(self, "_elements_src", None)))
+
+    # ---- reorder (src/index/reorder.rs) ----
+    def compute_order(self):
+        """Granne::compute_order (reorder.rs:126-174) on the GPU: order[i] == j moves element j to position i."""
+        order = np.zeros(len(self), dtype=np.uint64)
+        _check(load_library().granne_b200_compute_order(self._h, _ptr(order), order.size))
+        return order
+
+    def _reopen_reordered(self, order):
+        kind = self.element_kind
+        index_bytes = self._source_bytes(getattr(self, "_index_src", None))
+        elements_bytes = self._source_bytes(getattr(self, "_elements_src", None))
+        new_index, new_elements = apply_order(index_bytes, kind, elements_bytes, order)
+        emb = getattr(self, "_embeddings_src", None)
+        emb_bytes = self._source_bytes(emb) if emb is not None else None
+        fresh = Granne.from_bytes(new_index, kind, new_elements, emb_bytes, device=self.device)
+        self.close()
+        self.__dict__.update(fresh.__dict__)
+        fresh._h = None
+        return [int(x) for x in order]
+
+    def reorder(self, show_progress=False):
+        """Granne.reorder(show_progress) (py/src/lib.rs:311-315, reorder.rs:59-82): reorders index and elements in
+        place for locality; returns the permutation (new -> old)."""
+        return self._reopen_reordered(self.compute_order())
+
+    def reorder_by_keys(self, keys, show_progress=False):
+        """Granne::reorder_by_keys (reorder.rs:89-124): layer-preserving sort by `keys` (uint64 [n] or [n, kw])."""
+        return self._reopen_reordered(order_by_keys(self._source_bytes(self._index_src), keys))
 
     def close(self):
         if getattr(self, "_h", None):
@@ -349,6 +385,7 @@ class GranneBuilder:
         self._h = h
         self.device = device
         self._elements_bytes = elements_bytes
+        self._embeddings_bytes = embeddings_bytes
 
     def build(self, num_elements=0):
         """Builder::build() / build_partial(num_elements)."""
@@ -387,6 +424,7 @@ class GranneBuilder:
         image = self.index_bytes().tobytes()  # snapshot: later build() calls do not change this Granne
         g._index_src = ("bytes", image)
         g._elements_src = ("bytes", self._elements_bytes)
+        g._embeddings_src = ("bytes", self._embeddings_bytes) if self._embeddings_bytes is not None else None
         return g
 
     def save_elements(self, path):
@@ -441,6 +479,51 @@ def reencode_index(index_bytes):
     out = np.empty(need.value, dtype=np.uint8)
     _check(L.granne_b200_reencode_index(_ptr(ib), ib.size, _ptr(out), out.size, C.byref(need)))
     return out.tobytes()
+
+
+def order_from_trails(layer_lens, trails):
+    """Host-only: the sort half of compute_order for trails (uint32 [n, 8]) computed elsewhere."""
+    lens = np.ascontiguousarray(layer_lens, dtype=np.uint64)
+    t = np.ascontiguousarray(trails, dtype=np.uint32)
+    order = np.zeros(t.shape[0], dtype=np.uint64)
+    _check(load_library().granne_b200_order_from_trails(_ptr(lens), lens.size, _ptr(t), t.shape[0], _ptr(order)))
+    return order
+
+
+def order_by_keys(index_bytes, keys):
+    """Host-only: the layer-preserving sort of Granne::reorder_by_keys (reorder.rs:96-108)."""
+    ib = np.frombuffer(index_bytes, dtype=np.uint8)
+    k = np.ascontiguousarray(keys, dtype=np.uint64)
+    k = k.reshape(k.shape[0], -1)
+    order = np.zeros(k.shape[0], dtype=np.uint64)
+    _check(load_library().granne_b200_order_by_keys(_ptr(ib), ib.size, _ptr(k), k.shape[0], k.shape[1], _ptr(order)))
+    return order
+
+
+def compute_keys_for_reordering(elements_bytes, embeddings_bytes):
+    """Host-only: embeddings::compute_keys_for_reordering (embeddings/reorder.rs:31-58) -> uint64 [n, 8]."""
+    eb = np.frombuffer(elements_bytes, dtype=np.uint8)
+    mb = np.frombuffer(embeddings_bytes, dtype=np.uint8)
+    n = int(np.frombuffer(eb[:8].tobytes(), dtype=np.uint64)[0])
+    keys = np.zeros((n, 8), dtype=np.uint64)
+    _check(load_library().granne_b200_embedding_reorder_keys(_ptr(eb), eb.size, _ptr(mb), mb.size, _ptr(keys)))
+    return keys
+
+
+def apply_order(index_bytes, element_type, elements_bytes, order):
+    """Host-only: reorder_layers + Permutable::permute -> (index file image, elements file image) as bytes."""
+    L = load_library()
+    kind = element_type if isinstance(element_type, int) else _kind(element_type)
+    ib = np.frombuffer(index_bytes, dtype=np.uint8)
+    eb = np.frombuffer(elements_bytes, dtype=np.uint8)
+    o = np.ascontiguousarray(order, dtype=np.uint64)
+    n_i, n_e = C.c_size_t(), C.c_size_t()
+    _check(L.granne_b200_apply_order(_ptr(ib), ib.size, kind, _ptr(eb), eb.size, _ptr(o), o.size, None, 0,
+                                     C.byref(n_i), None, 0, C.byref(n_e)))
+    oi, oe = np.empty(n_i.value, dtype=np.uint8), np.empty(n_e.value, dtype=np.uint8)
+    _check(L.granne_b200_apply_order(_ptr(ib), ib.size, kind, _ptr(eb), eb.size, _ptr(o), o.size, _ptr(oi), oi.size,
+                                     C.byref(n_i), _ptr(oe), oe.size, C.byref(n_e)))
+    return oi.tobytes(), oe.tobytes()
 
 
 def decode_layer(index_bytes, layer):

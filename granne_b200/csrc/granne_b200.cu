@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "formats.hpp"
+#include "reorder.hpp"
 #include "build_kernels.cuh"
 #include "search_kernels.cuh"
 
@@ -1296,6 +1297,170 @@ int granne_b200_reencode_index(const void* index_bytes, size_t index_len, void* 
         if (!out) return GRANNE_B200_OK;
         if (cap < image.size()) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "output buffer too small");
         std::memcpy(out, image.data(), image.size());
+        return GRANNE_B200_OK;
+    } catch (const std::exception& e) {
+        return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, std::string("exception: ") + e.what());
+    }
+}
+
+// ---- reorder (src/index/reorder.rs) -----------------------------------------------------------------------------------
+
+// Granne::compute_order (reorder.rs:126-174).  The trail of element idx (find_entrypoint_trail, reorder.rs:180-207) is
+// one max_search = 1 search_for_neighbors from node 0 in each of the first min(8, layer) layers: here, per trail layer,
+// ONE batch of the search kernel over a single-layer view of the staged graph, queries given by element id.
+int granne_b200_compute_order(granne_b200_index* h, uint64_t* order_out, uint64_t cap) {
+    if (!h || !order_out) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "null argument");
+    const uint64_t n = h->index_len;
+    if (cap < n) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "order buffer shorter than Index::len");
+    const int nl = h->dev.num_layers;
+    if (nl == 0) return GRANNE_B200_OK;
+    try {
+        GB_CUDA(cudaSetDevice(h->device));
+        std::vector<uint64_t> layer_lens(nl);
+        for (int l = 0; l < nl; ++l) layer_lens[l] = h->dev.layer_len[l];
+        const size_t trail_layers = std::min<size_t>(gb::kTrailLayers, (size_t)nl - 1);
+        std::vector<std::vector<uint32_t>> eps(trail_layers);
+        Workspace* w = nullptr;
+        int rc = ws_acquire(h, &w);
+        if (rc) return rc;
+        const size_t batch = (size_t)std::min<uint64_t>(std::max<uint64_t>(n, 1), 1u << 20);
+        uint32_t *d_q = nullptr, *d_ids = nullptr, *d_cnt = nullptr;
+        float* d_d = nullptr;
+        const gb::DeviceIndex saved = h->dev;
+        struct Cleanup {  // reorder is `&mut self` in the reference: no concurrent searches while the view is swapped
+            Handle* h;
+            Workspace* w;
+            const gb::DeviceIndex* saved;
+            uint32_t **q, **ids, **cnt;
+            float** d;
+            ~Cleanup() {
+                h->dev = *saved;
+                cudaFree(*q);
+                cudaFree(*ids);
+                cudaFree(*cnt);
+                cudaFree(*d);
+                ws_release(h, w);
+            }
+        } cleanup{h, w, &saved, &d_q, &d_ids, &d_cnt, &d_d};
+        GB_CUDA(cudaMalloc(&d_q, batch * 4));
+        GB_CUDA(cudaMalloc(&d_ids, batch * 4));
+        GB_CUDA(cudaMalloc(&d_cnt, batch * 4));
+        GB_CUDA(cudaMalloc(&d_d, batch * 4));
+        for (size_t j = 0; j < trail_layers; ++j) {
+            eps[j].resize(n - layer_lens[j]);
+            h->dev.num_layers = 1;
+            h->dev.layer_rows[0] = saved.layer_rows[j];
+            h->dev.layer_width[0] = saved.layer_width[j];
+            h->dev.layer_len[0] = saved.layer_len[j];
+            for (uint64_t base = layer_lens[j]; base < n; base += batch) {
+                const uint64_t bsz = std::min<uint64_t>(batch, n - base);
+                gb::iota_kernel<<<(unsigned)((bsz + 255) / 256), 256, 0, w->stream>>>(d_q, (uint32_t)bsz, (uint32_t)base, 1);
+                h->launches++;
+                rc = enqueue_search(h, w, d_q, bsz, gb::kQueryById, 1, 1, d_ids, d_d, d_cnt, nullptr, w->stream, true);
+                if (rc) return rc;
+                GB_CUDA(cudaMemcpyAsync(eps[j].data() + (base - layer_lens[j]), d_ids, bsz * 4, cudaMemcpyDeviceToHost,
+                                        w->stream));
+                int herr[4] = {0, 0, 0, 0};
+                GB_CUDA(cudaMemcpyAsync(herr, w->d_error, sizeof(herr), cudaMemcpyDeviceToHost, w->stream));
+                GB_CUDA(cudaStreamSynchronize(w->stream));
+                if ((rc = error_from_bits(herr[0]))) return rc;
+            }
+        }
+        h->dev = saved;
+        gb::order_from_trails(layer_lens, eps, order_out);
+        return GRANNE_B200_OK;
+    } catch (const std::exception& e) {
+        return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, std::string("exception: ") + e.what());
+    }
+}
+
+int granne_b200_order_from_trails(const uint64_t* layer_lens, uint32_t num_layers, const uint32_t* trails, uint64_t n,
+                                  uint64_t* order_out) {
+    if (!layer_lens || !trails || !order_out) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "null argument");
+    try {
+        std::vector<uint64_t> lens(layer_lens, layer_lens + num_layers);
+        if (num_layers == 0 || lens.back() != n) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "n must equal the last layer's length");
+        for (uint32_t l = 1; l < num_layers; ++l)
+            if (lens[l] < lens[l - 1]) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "layer lengths must not decrease");
+        const size_t trail_layers = std::min<size_t>(gb::kTrailLayers, (size_t)num_layers - 1);
+        std::vector<std::vector<uint32_t>> eps(trail_layers);
+        for (size_t j = 0; j < trail_layers; ++j) {
+            eps[j].resize(n - lens[j]);
+            for (uint64_t idx = lens[j]; idx < n; ++idx) {
+                const uint32_t v = trails[idx * gb::kTrailLayers + j];
+                if (v >= lens[j]) return fail(GRANNE_B200_ERR_OUT_OF_RANGE, "trail entry outside its layer");
+                eps[j][idx - lens[j]] = v;
+            }
+        }
+        gb::order_from_trails(lens, eps, order_out);
+        return GRANNE_B200_OK;
+    } catch (const std::exception& e) {
+        return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, std::string("exception: ") + e.what());
+    }
+}
+
+int granne_b200_order_by_keys(const void* index_bytes, size_t index_len, const uint64_t* keys, uint64_t num_keys,
+                              uint32_t key_width, uint64_t* order_out) {
+    if (!index_bytes || !keys || !order_out || key_width == 0)
+        return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "null argument");
+    try {
+        gb::HostGraph graph;
+        std::string err;
+        if (!gb::parse_index(static_cast<const uint8_t*>(index_bytes), index_len, &graph, &err))
+            return fail(GRANNE_B200_ERR_FORMAT, err);
+        std::vector<uint64_t> layer_lens;
+        for (const gb::HostLayer& L : graph.layers) layer_lens.push_back(L.num_nodes);
+        if (num_keys != (layer_lens.empty() ? 0 : layer_lens.back()))  // assert_eq!(self.len(), keys.len())
+            return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "number of keys must equal Index::len");
+        gb::order_by_keys(layer_lens, keys, key_width, order_out);
+        return GRANNE_B200_OK;
+    } catch (const std::exception& e) {
+        return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, std::string("exception: ") + e.what());
+    }
+}
+
+int granne_b200_embedding_reorder_keys(const void* elements_bytes, size_t elements_len, const void* embeddings_bytes,
+                                       size_t embeddings_len, uint64_t* keys_out) {
+    if (!elements_bytes || !embeddings_bytes || !keys_out) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "null argument");
+    try {
+        std::string err;
+        if (!gb::embedding_reorder_keys(static_cast<const uint8_t*>(elements_bytes), elements_len,
+                                        static_cast<const uint8_t*>(embeddings_bytes), embeddings_len, keys_out, &err))
+            return fail(GRANNE_B200_ERR_FORMAT, err);
+        return GRANNE_B200_OK;
+    } catch (const std::exception& e) {
+        return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, std::string("exception: ") + e.what());
+    }
+}
+
+int granne_b200_apply_order(const void* index_bytes, size_t index_len, int element_kind, const void* elements_bytes,
+                            size_t elements_len, const uint64_t* order, uint64_t n, void* out_index, size_t index_cap,
+                            size_t* index_out_len, void* out_elements, size_t elements_cap, size_t* elements_out_len) {
+    if (!index_bytes || !elements_bytes || !order || !index_out_len || !elements_out_len)
+        return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "null argument");
+    try {
+        gb::HostGraph graph;
+        std::string err;
+        if (!gb::parse_index(static_cast<const uint8_t*>(index_bytes), index_len, &graph, &err))
+            return fail(GRANNE_B200_ERR_FORMAT, err);
+        std::vector<uint8_t> image, elements;
+        if (!gb::reorder_graph(graph, order, n, &image, &err)) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, err);
+        const uint8_t* eb = static_cast<const uint8_t*>(elements_bytes);
+        bool ok;
+        switch (element_kind) {
+            case GRANNE_B200_ANGULAR: ok = gb::permute_dense(eb, elements_len, 4, order, n, &elements, &err); break;
+            case GRANNE_B200_ANGULAR_INT: ok = gb::permute_dense(eb, elements_len, 1, order, n, &elements, &err); break;
+            case GRANNE_B200_EMBEDDINGS: ok = gb::permute_sum_elements(eb, elements_len, order, n, &elements, &err); break;
+            default: return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "unknown element kind");
+        }
+        if (!ok) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, err);
+        *index_out_len = image.size();
+        *elements_out_len = elements.size();
+        if (!out_index && !out_elements) return GRANNE_B200_OK;
+        if (!out_index || !out_elements || index_cap < image.size() || elements_cap < elements.size())
+            return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "output buffer too small");
+        std::memcpy(out_index, image.data(), image.size());
+        std::memcpy(out_elements, elements.data(), elements.size());
         return GRANNE_B200_OK;
     } catch (const std::exception& e) {
         return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, std::string("exception: ") + e.what());

@@ -240,6 +240,38 @@ int granne_b200_elements_from_raw(int element_kind, const float* raw, uint64_t n
  * to the input; used to test the writer without a device.  Call with out == NULL to query the size. */
 int granne_b200_reencode_index(const void* index_bytes, size_t index_len, void* out, size_t cap, size_t* out_len);
 
+/* ---- Granne::reorder / reorder_by_keys (src/index/reorder.rs:59-174) ---------------------------------------------
+ * An order is `order[i] == j`: the node and element at old index j move to index i (reorder.rs:66-67). */
+
+/* Granne::compute_order (reorder.rs:126-174): for every element above the first layer, the trail of closest nodes in
+ * the layers above it (find_entrypoint_trail, reorder.rs:180-207 — max_search = 1 searches from node 0), computed as
+ * batches of the search kernel; then the per-layer sort by (trail, idx).  `order_out` holds Index::len entries.  Like
+ * the reference's `&mut self`, not to be called concurrently with searches on `h`. */
+int granne_b200_compute_order(granne_b200_index* h, uint64_t* order_out, uint64_t cap);
+
+/* Host-only.  The sort half of compute_order (reorder.rs:133-166) for trails computed elsewhere: `trails` is n rows of
+ * 8 node ids, row idx = find_entrypoint_trail of element idx (entries past min(8, first layer of idx) ignored). */
+int granne_b200_order_from_trails(const uint64_t* layer_lens, uint32_t num_layers, const uint32_t* trails, uint64_t n,
+                                  uint64_t* order_out);
+
+/* Host-only.  The ordering part of Granne::reorder_by_keys (reorder.rs:96-108): a layer-preserving sort by
+ * (key, idx); `keys` is num_keys rows of key_width u64 compared lexicographically. */
+int granne_b200_order_by_keys(const void* index_bytes, size_t index_len, const uint64_t* keys, uint64_t num_keys,
+                              uint32_t key_width, uint64_t* order_out);
+
+/* Host-only.  embeddings::compute_keys_for_reordering (src/elements/embeddings/reorder.rs:31-58): keys_out holds
+ * num_elements rows of 8 u64 (embedding ids by decreasing norm, zero padded). */
+int granne_b200_embedding_reorder_keys(const void* elements_bytes, size_t elements_len, const void* embeddings_bytes,
+                                       size_t embeddings_len, uint64_t* keys_out);
+
+/* Host-only.  reorder_layers (reorder.rs:209-292) + Permutable::permute (src/slice_vector/mod.rs:437-458,
+ * src/elements/embeddings/mod.rs:191-217): writes the reordered index file image and the permuted elements file image.
+ * Call with both output pointers NULL to query the sizes.  An order that is not a layer-preserving permutation (the
+ * reference panics) returns GRANNE_B200_ERR_INVALID_ARGUMENT. */
+int granne_b200_apply_order(const void* index_bytes, size_t index_len, int element_kind, const void* elements_bytes,
+                            size_t elements_len, const uint64_t* order, uint64_t n, void* out_index, size_t index_cap,
+                            size_t* index_out_len, void* out_elements, size_t elements_cap, size_t* elements_out_len);
+
 /* Number of kernels this library launched on behalf of `h` since it was opened (bench.py's gpu_launches). */
 uint64_t granne_b200_launch_count(const granne_b200_index* h);
 
