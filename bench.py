@@ -56,6 +56,8 @@ def parse_args():
                          "NVLink peer memory); nccl = one all-gather per step")
     ap.add_argument("--kind", default="angular", choices=["angular", "angular_int"],
                     help="element type (angular_int = BASELINE config 3 style i8/dp4a path)")
+    ap.add_argument("--reorder", type=int, default=0,
+                    help="1: run Granne::reorder (GPU compute_order + host apply) on the built index before searching")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target duration of the cpu_baseline sample")
     return ap.parse_args()
 
@@ -84,7 +86,8 @@ def workload_config(a, impl):
             "n": a.n, "dim": a.dim, "max_search": a.max_search,
             "k": a.k, "queries_per_step_per_gpu": a.nq, "index": "replicated, queries sharded" if a.gpus > 1
             else "single GPU", "l2": "inputs larger than L2 (%.0f MB vectors + adjacency; query batches rotate)"
-            % (a.n * a.dim * (4 if a.kind == "angular" else 1) / 1e6), "streams": a.streams, "impl": impl}
+            % (a.n * a.dim * (4 if a.kind == "angular" else 1) / 1e6), "streams": a.streams, "impl": impl,
+            "reordered": bool(getattr(a, "reorder", 0))}
 
 
 class ClockSampler:
@@ -258,6 +261,13 @@ def main():
             index = builder.get_index()
         builder_launches = 0
     t_build = time.time() - t0
+    t_reorder = None
+    if a.reorder and world == 1 and index_bytes is not None:
+        t0 = time.time()
+        index.reorder()
+        t_reorder = time.time() - t0
+        index_bytes = np.frombuffer(index.index_bytes(), dtype=np.uint8)
+        elements_bytes = np.frombuffer(index.elements_bytes(), dtype=np.uint8)
     if world > 1:
         size = torch.tensor([len(index_bytes) if rank == 0 else 0], dtype=torch.int64, device=dev)
         dist.broadcast(size, 0)
@@ -509,7 +519,7 @@ def main():
                      "solo_launch_ms": solo_ms,
                      "solo_launch_gbs": bytes_per_query * a.nq / (solo_ms / 1e3) / 1e9},
         "cpu_baseline": cpu,
-        "setup_s": {"data+elements": t_data, "gpu_index_build": t_build},
+        "setup_s": {"data+elements": t_data, "gpu_index_build": t_build, "reorder": t_reorder},
         "host_issue_ms_per_step": issue_ms / a.steps, "cuda_graphs": bool(graphs[0] is not None),
         "multi_gpu_gather": None if world == 1 else ("p2p peer stores fused into the search kernels" if fused is not None
                                                      else "nccl all_gather"),

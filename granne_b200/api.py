@@ -160,16 +160,24 @@ class Granne:
             return value()
         return bytes(value)
 
+    def index_bytes(self):
+        """Index::write_index (src/index/io.rs:11-70) into memory."""
+        return reencode_index(self._source_bytes(getattr(self, "_index_src", None)))
+
+    def elements_bytes(self):
+        """The elements file image (u64 dim + rows, src/slice_vector/mod.rs:460-466; offsets + 3-byte ids for
+        "embeddings")."""
+        return self._source_bytes(getattr(self, "_elements_src", None))
+
     def save_index(self, path):
-        """Granne.save_index(path) (py/src/lib.rs:325-329): Index::write_index of the loaded graph."""
+        """Granne.save_index(path) (py/src/lib.rs:325-329)."""
         with open(path, "wb") as f:
-            f.write(reencode_index(self._source_bytes(getattr(self, "_index_src", None))))
+            f.write(self.index_bytes())
 
     def save_elements(self, path):
-        """Granne.save_elements(path) (py/src/lib.rs:339-343): the elements file (u64 dim + rows,
-        src/slice_vector/mod.rs:460-466; offsets + 3-byte ids for "embeddings")."""
+        """Granne.save_elements(path) (py/src/lib.rs:339-343)."""
         with open(path, "wb") as f:
-            f.write(self._source_bytes(getattr(self, "_elements_src", None)))
+            f.write(self.elements_bytes())
 
     # ---- reorder (src/index/reorder.rs) ----
     def compute_order(self):
