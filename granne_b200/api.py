@@ -59,6 +59,7 @@ def load_library():
         "granne_b200_merge_topk_device": (i32, [i32, vp, vp, vp, sz, sz, u32, vp, vp, vp]),
         "granne_b200_inspect_index": (i32, [vp, sz, vp, vp, vp, vp, sz]),
         "granne_b200_decode_layer": (i32, [vp, sz, u64, vp, sz]),
+        "granne_b200_write_index": (i32, [vp, vp, sz, C.POINTER(sz)]),
         "granne_b200_reencode_index": (i32, [vp, sz, vp, sz, C.POINTER(sz)]),
         "granne_b200_compute_order": (i32, [vp, vp, u64]),
         "granne_b200_order_from_trails": (i32, [vp, u32, vp, u64, vp]),
@@ -125,7 +126,6 @@ class Granne:
                                         C.byref(h)))
         self._h = h
         self.device = device
-        self._index_src = ("path", index_path)
         self._elements_src = ("path", elements_path)
         self._embeddings_src = ("path", embeddings_path) if embeddings_path else None
 
@@ -143,7 +143,6 @@ class Granne:
                                   C.byref(h)))
         self._h = h
         self.device = device
-        self._index_src = ("bytes", index_bytes)
         self._elements_src = ("bytes", elements_bytes)
         self._embeddings_src = ("bytes", embeddings_bytes) if embeddings_bytes is not None else None
         return self
@@ -156,13 +155,16 @@ class Granne:
         if kind == "path":
             with open(value, "rb") as f:
                 return f.read()
-        if kind == "call":
-            return value()
         return bytes(value)
 
     def index_bytes(self):
-        """Index::write_index (src/index/io.rs:11-70) into memory."""
-        return reencode_index(self._source_bytes(getattr(self, "_index_src", None)))
+        """Index::write_index (src/index/io.rs:11-70) into memory, from the staged graph."""
+        L = load_library()
+        need = C.c_size_t()
+        _check(L.granne_b200_write_index(self._h, None, 0, C.byref(need)))
+        out = np.empty(need.value, dtype=np.uint8)
+        _check(L.granne_b200_write_index(self._h, _ptr(out), out.size, C.byref(need)))
+        return out[:need.value].tobytes()
 
     def elements_bytes(self):
         """The elements file image (u64 dim + rows, src/slice_vector/mod.rs:460-466; offsets + 3-byte ids for
@@ -188,7 +190,7 @@ class Granne:
 
     def _reopen_reordered(self, order):
         kind = self.element_kind
-        index_bytes = self._source_bytes(getattr(self, "_index_src", None))
+        index_bytes = self.index_bytes()
         elements_bytes = self._source_bytes(getattr(self, "_elements_src", None))
         new_index, new_elements = apply_order(index_bytes, kind, elements_bytes, order)
         emb = getattr(self, "_embeddings_src", None)
@@ -206,7 +208,7 @@ class Granne:
 
     def reorder_by_keys(self, keys, show_progress=False):
         """Granne::reorder_by_keys (reorder.rs:89-124): layer-preserving sort by `keys` (uint64 [n] or [n, kw])."""
-        return self._reopen_reordered(order_by_keys(self._source_bytes(self._index_src), keys))
+        return self._reopen_reordered(order_by_keys(self.index_bytes(), keys))
 
     def close(self):
         if getattr(self, "_h", None):
@@ -429,8 +431,6 @@ class GranneBuilder:
         g = Granne.__new__(Granne)
         g._h = h
         g.device = self.device
-        image = self.index_bytes().tobytes()  # snapshot: later build() calls do not change this Granne
-        g._index_src = ("bytes", image)
         g._elements_src = ("bytes", self._elements_bytes)
         g._embeddings_src = ("bytes", self._embeddings_bytes) if self._embeddings_bytes is not None else None
         return g

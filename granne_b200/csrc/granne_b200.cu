@@ -1171,18 +1171,19 @@ int granne_b200_builder_get_neighbors(const granne_b200_builder* b, uint64_t idx
     return granne_b200_get_neighbors(b->h.get(), idx, layer, out, cap, n_out);
 }
 
-int granne_b200_builder_write_index(granne_b200_builder* b, void* out, size_t cap, size_t* out_len) {
-    if (!b || !out_len) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "null argument");
+// Index::write_index (src/index/io.rs:11-70) from the staged fixed-width rows of any handle.
+int granne_b200_write_index(const granne_b200_index* h, void* out, size_t cap, size_t* out_len) {
+    if (!h || !out_len) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "null argument");
     try {
-        Handle* h = b->h.get();
         GB_CUDA(cudaSetDevice(h->device));
         std::vector<std::vector<uint32_t>> host(h->dev.num_layers);
         std::vector<gb::LayerView> views;
         for (int l = 0; l < h->dev.num_layers; ++l) {
-            const size_t n = (size_t)h->dev.layer_len[l] * b->stride;
+            const uint32_t stride = h->dev.layer_width[l];
+            const size_t n = (size_t)h->dev.layer_len[l] * stride;
             host[l].resize(n);
             if (n) GB_CUDA(cudaMemcpy(host[l].data(), h->dev.layer_rows[l], n * 4, cudaMemcpyDeviceToHost));
-            views.push_back({host[l].data(), h->dev.layer_len[l], b->stride});
+            views.push_back({host[l].data(), h->dev.layer_len[l], stride});
         }
         std::vector<uint8_t> image;
         std::string err;
@@ -1195,6 +1196,11 @@ int granne_b200_builder_write_index(granne_b200_builder* b, void* out, size_t ca
     } catch (const std::exception& e) {
         return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, std::string("exception: ") + e.what());
     }
+}
+
+int granne_b200_builder_write_index(granne_b200_builder* b, void* out, size_t cap, size_t* out_len) {
+    if (!b) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "null argument");
+    return granne_b200_write_index(b->h.get(), out, cap, out_len);
 }
 
 int granne_b200_builder_get_index(granne_b200_builder* b, granne_b200_index** out) {

@@ -235,6 +235,10 @@ void granne_b200_builder_free(granne_b200_builder* b);
 int granne_b200_elements_from_raw(int element_kind, const float* raw, uint64_t n, uint32_t dim, int device, void* out,
                                   size_t cap, size_t* out_len);
 
+/* Index::write_index (src/index/io.rs:11-70; py Granne.save_index, py/src/lib.rs:325-329) for a loaded or
+ * builder-snapshot index: the granne index file image written from the staged rows.  out == NULL queries the size. */
+int granne_b200_write_index(const granne_b200_index* h, void* out, size_t cap, size_t* out_len);
+
 /* Host-only: decodes an index image and writes it again with this library's writer (Index::write_index,
  * src/index/io.rs:11-70).  For an image written by granne (sorted lists, same coding rules) the output is byte-identical
  * to the input; used to test the writer without a device.  Call with out == NULL to query the size. */
