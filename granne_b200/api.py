@@ -512,7 +512,9 @@ def compute_keys_for_reordering(elements_bytes, embeddings_bytes):
     """Host-only: embeddings::compute_keys_for_reordering (embeddings/reorder.rs:31-58) -> uint64 [n, 8]."""
     eb = np.frombuffer(elements_bytes, dtype=np.uint8)
     mb = np.frombuffer(embeddings_bytes, dtype=np.uint8)
-    n = int(np.frombuffer(eb[:8].tobytes(), dtype=np.uint64)[0])
+    n = int(np.frombuffer(eb[:8].tobytes(), dtype=np.uint64)[0]) if eb.size >= 8 else -1
+    if n < 0 or 8 + (n + 1) * 5 > eb.size:  # u64 count | (count + 1) five-byte offsets | ids
+        raise GranneError(-2, "embeddings elements file: offset table exceeds the file")
     keys = np.zeros((n, 8), dtype=np.uint64)
     _check(load_library().granne_b200_embedding_reorder_keys(_ptr(eb), eb.size, _ptr(mb), mb.size, _ptr(keys)))
     return keys
