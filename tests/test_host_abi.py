@@ -138,3 +138,36 @@ def test_writer_round_trips_the_golden_images(lib):
     for path in glob.glob(os.path.join(ROOT, "tests", "golden", "*.npz")):
         image = np.load(path)["index"].tobytes()
         assert api.reencode_index(image) == image
+
+
+def test_header_is_plain_c_and_links_from_c(lib, tmp_path):
+    # the boundary is a C ABI: the header compiles as strict C99 and a C program links against the shared library
+    import shutil
+    import subprocess
+
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "client.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "granne_b200.h"
+int main(void) {
+    granne_b200_index* h = NULL;
+    uint64_t layers = 99;
+    unsigned char junk[16] = {0};
+    if (granne_b200_abi_version() != GRANNE_B200_ABI_VERSION) return 1;
+    if (granne_b200_inspect_index(junk, sizeof junk, &layers, NULL, NULL, NULL, 0) != GRANNE_B200_ERR_FORMAT) return 2;
+    if (strlen(granne_b200_last_error()) == 0) return 3;
+    if (granne_b200_open(NULL, 0, GRANNE_B200_ANGULAR, NULL, 0, NULL, 0, 0, &h) == GRANNE_B200_OK) return 4;
+    if (granne_b200_len(NULL) != 0) return 5;
+    printf("ok\n");
+    return 0;
+}
+''')
+    exe = str(tmp_path / "client")
+    libdir = os.path.dirname(api.library_path())
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I" + os.path.join(ROOT, "include"),
+                           str(src), "-o", exe, "-L" + libdir, "-lgranne_b200", "-Wl,-rpath," + libdir])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip() == "ok", (r.returncode, r.stdout, r.stderr)
