@@ -1,6 +1,7 @@
-// formats.hpp — host-side readers for granne's on-disk formats, decoding straight into the HBM staging layout.
+// formats.hpp — host-side readers and writers for granne's on-disk formats.  Readers decode straight into the HBM
+// staging layout; the writer (encode_index, bottom of this file) produces granne index files from staged rows.
 //
-// Read side only: the index file (src/index/io.rs:72-113), the compressed layer blobs
+// Read side: the index file (src/index/io.rs:72-113), the compressed layer blobs
 // (src/slice_vector/offsets.rs:127-139,148-218,249-259; src/slice_vector/set_vector.rs:91-115,158-162), dense vector
 // files (src/slice_vector/mod.rs:213-221) and SumEmbeddings element files (src/slice_vector/mod.rs:660-676,
 // src/odd_byte_int.rs:3-36).  Nothing here is shared with oracle/ (the oracle is test infrastructure).

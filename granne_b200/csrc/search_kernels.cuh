@@ -2,14 +2,22 @@
 //   Granne::search -> find_entrypoint -> search_for_neighbors -> ElementContainer::dist_to_element
 //   (reference: src/index/mod.rs:140-150, 962-1037; src/max_size_heap.rs; src/elements/*; src/math.rs)
 //
-// Execution model: one warp per query (one 32-thread CTA, several CTAs per SM, persistent over a work counter).
-// Per query the warp owns, in shared memory,
-//   * a sorted candidate list L (capacity C = max_search + slack) that merges the reference's two heaps:
-//     `res` (bounded max-heap of expanded nodes) and `pq` (unbounded min-heap frontier) — see "Exactness" below,
-//   * an exact visited set (open-addressing hash of u32 ids; the reference's FxHashSet),
-//   * a 32x36 f32 tile used to reproduce the reference's strictly ordered 32-lane partial-sum reduction.
-// Candidate vectors are gathered straight from HBM with fully coalesced 128-bit loads (the row layout in HBM is
-// lane-permuted so that one LDG.128 per lane fetches a whole 512-byte row), all rows of one expansion in flight at once.
+// Execution model: one warp per query (one 32-thread CTA, GB_MIN_BLOCKS resident CTAs per SM, persistent over a
+// work counter).  Per query the warp owns
+//   * in shared memory, a sorted candidate list L that merges the reference's two heaps: `res` (bounded max-heap of
+//     expanded nodes) and `pq` (unbounded min-heap frontier) — see "Exactness" below.  Fast pass (search_layer_fast):
+//     split u32 arrays Ld (distance bits | expanded flag) / Li (ids), capacity 32*R; slow pass (search_layer): 64-bit
+//     keys in a global-memory workspace, for the rare query whose plateau of equal distances overflows the fast list;
+//   * an exact visited set (the reference's FxHashSet): fast pass = a bucketed table in global memory that stays L2
+//     resident (8 ids per 32-byte bucket, one sector read per neighbour, no atomics — the warp is the only writer);
+//     slow pass = open addressing with CAS in the global workspace;
+//   * an 8-row x 36-float tile in shared memory used to reproduce the reference's strictly ordered 32-lane
+//     partial-sum reduction, plus a staging tile for candidate rows.
+// Candidate rows are gathered from HBM with 1-D bulk copies (cp.async.bulk -> UBLKCP, completion on an mbarrier with
+// expect_tx), all rows of a batch in flight at once; the f32 row layout in HBM is lane-permuted so that lane i reads
+// its accumulator chunks with 128-bit shared loads.  Element rows use an L2 evict_first policy, adjacency rows and the
+// visited table evict_last; the adjacency row of the runner-up candidate is fetched speculatively while the current
+// expansion's distances are computed.
 //
 // Exactness (bit-identical ids AND f32 distances, identical n_dist / n_expand counters):
 //   * dot_product_f32 (src/math.rs:16-42): lane i owns accumulator chunk[i]; FMA over chunks in order; the 32
