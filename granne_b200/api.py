@@ -59,6 +59,7 @@ def load_library():
         "granne_b200_merge_topk_device": (i32, [i32, vp, vp, vp, sz, sz, u32, vp, vp, vp]),
         "granne_b200_inspect_index": (i32, [vp, sz, vp, vp, vp, vp, sz]),
         "granne_b200_decode_layer": (i32, [vp, sz, u64, vp, sz]),
+        "granne_b200_compute_distances": (i32, [i32, vp, vp, u64, u32, i32, vp]),
         "granne_b200_write_index": (i32, [vp, vp, sz, C.POINTER(sz)]),
         "granne_b200_reencode_index": (i32, [vp, sz, vp, sz, C.POINTER(sz)]),
         "granne_b200_compute_order": (i32, [vp, vp, u64]),
@@ -487,6 +488,26 @@ def reencode_index(index_bytes):
     out = np.empty(need.value, dtype=np.uint8)
     _check(L.granne_b200_reencode_index(_ptr(ib), ib.size, _ptr(out), out.size, C.byref(need)))
     return out.tobytes()
+
+
+def compute_distances(element_type, a, b, device=0):
+    """n pairwise distances Vector::from(a_i).dist(&Vector::from(b_i)) on the GPU; a, b: (n, dim) raw float32."""
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    b = np.ascontiguousarray(b, dtype=np.float32)
+    if a.ndim != 2 or a.shape != b.shape:
+        raise ValueError("a and b must both have shape (n, dim)")
+    out = np.empty(a.shape[0], dtype=np.float32)
+    _check(load_library().granne_b200_compute_distances(_kind(element_type), _ptr(a), _ptr(b), a.shape[0], a.shape[1],
+                                                        device, _ptr(out)))
+    return out
+
+
+def compute_distance(element_type, a, b, device=0):
+    """granne.compute_distance(element_type, a, b) (py/src/lib.rs:71-89)."""
+    if element_type not in ("angular", "angular_int"):
+        raise ValueError("Unsupported element type")
+    return float(compute_distances(element_type, np.asarray(a, dtype=np.float32)[None, :],
+                                   np.asarray(b, dtype=np.float32)[None, :], device)[0])
 
 
 def order_from_trails(layer_lens, trails):

@@ -303,6 +303,43 @@ __global__ void __launch_bounds__(32) build_prune_kernel(const DeviceIndex ix, c
     }
 }
 
+// Dist::dist between caller-supplied vectors (py compute_distance, py/src/lib.rs:71-89: `Vector::from(a).dist(
+// &Vector::from(b))`): the b vectors are staged as the element container, a_i arrives as a raw query (normalised /
+// quantised by prepare_query exactly like Vector::from) and pair i is dist_to_element(i, a_i).  One warp per pair.
+struct PairArgs {
+    const void* queries;  // n x dim raw f32
+    uint32_t n;
+    float* out;           // n distances
+    int* error_flag;
+    uint32_t stg_rows;
+    uint32_t stg_row_bytes;
+    uint32_t tile_rows;
+};
+
+template <class Dist>
+__global__ void __launch_bounds__(32) pair_distance_kernel(const DeviceIndex ix, const PairArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WarpCtx c;
+    LinkScratch s;
+    setup_ctx<Dist>(ix, c, s, smem_raw, a.stg_rows, a.stg_row_bytes, a.tile_rows, 8);
+    Dist dist;
+    SearchArgs q{};
+    q.queries = a.queries;
+    q.query_format = kQueryRawF32;
+    for (uint32_t i = blockIdx.x; i < a.n; i += gridDim.x) {
+        c.status = 0;
+        c.q_norm_i8 = 0;
+        prepare_query(ix, q, c, i);
+        dist.load_query(ix, c);
+        const float d = dist.dists(ix, c, i, 1);
+        if (__any_sync(kFullMask, c.status & kStatusNotFinite)) {
+            if (c.lane == 0) atomicOr(a.error_flag, kStatusNotFinite);
+        }
+        if (c.lane == 0) a.out[i] = d;
+        __syncwarp();
+    }
+}
+
 // ids[i] = start + i * step  (step = +1 ascending insert pass, -1 for the reinsertion pass: reverse order, :776-782)
 __global__ void iota_kernel(uint32_t* ids, uint32_t n, uint32_t start, int step) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -642,6 +642,23 @@ struct DistDispatch {
     }
 };
 
+struct PairLaunch {
+    Handle* h;
+    gb::PairArgs a;
+    size_t smem;
+    unsigned grid;
+    cudaStream_t stream;
+    template <class Dist>
+    int run() {
+        auto k = gb::pair_distance_kernel<Dist>;
+        GB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
+        k<<<grid, 32, smem, stream>>>(h->dev, a);
+        h->launches++;
+        GB_CUDA(cudaGetLastError());
+        return GRANNE_B200_OK;
+    }
+};
+
 struct LinkLaunch {
     Handle* h;
     gb::BuildArgs a;
@@ -1286,6 +1303,65 @@ int granne_b200_elements_from_raw(int element_kind, const float* raw, uint64_t n
     cudaFree(d_raw);
     cudaFree(d_out);
     return rc;
+}
+
+// ---- compute_distance (py/src/lib.rs:71-89) -----------------------------------------------------------------------
+int granne_b200_compute_distances(int element_kind, const float* a, const float* b, uint64_t n, uint32_t dim, int device,
+                                  float* out) {
+    if (n == 0) return GRANNE_B200_OK;
+    if (!a || !b || !out) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "null argument");
+    if (n > 0xFFFFFFFFull) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "too many pairs for one call");
+    try {
+        // the b vectors become an element container (Vector::from per row, on the device) ...
+        size_t need = 0;
+        int rc = granne_b200_elements_from_raw(element_kind, nullptr, n, dim, device, nullptr, 0, &need);
+        if (rc) return rc;
+        std::vector<uint8_t> elements(need);
+        if ((rc = granne_b200_elements_from_raw(element_kind, b, n, dim, device, elements.data(), need, &need))) return rc;
+        // ... behind an index without layers
+        std::vector<uint8_t> image;
+        std::string err;
+        if (!gb::encode_index({}, &image, &err)) return fail(GRANNE_B200_ERR_FORMAT, err);
+        Handle* raw_h = nullptr;
+        if ((rc = open_impl(image.data(), image.size(), element_kind, elements.data(), elements.size(), nullptr, 0, device,
+                            &raw_h)))
+            return rc;
+        std::unique_ptr<Handle, void (*)(Handle*)> h(raw_h, [](Handle* p) { granne_b200_close(p); });
+        const LaunchPlan plan = make_plan(h.get(), 1);
+        float *d_a = nullptr, *d_out = nullptr;
+        int* d_err = nullptr;
+        struct Free {
+            float **a, **o;
+            int** e;
+            ~Free() {
+                cudaFree(*a);
+                cudaFree(*o);
+                cudaFree(*e);
+            }
+        } guard{&d_a, &d_out, &d_err};
+        GB_CUDA(cudaMalloc(&d_a, (size_t)n * dim * 4));
+        GB_CUDA(cudaMalloc(&d_out, (size_t)n * 4));
+        GB_CUDA(cudaMalloc(&d_err, 4));
+        GB_CUDA(cudaMemcpy(d_a, a, (size_t)n * dim * 4, cudaMemcpyHostToDevice));
+        GB_CUDA(cudaMemset(d_err, 0, 4));
+        PairLaunch L{h.get(), {}, plan.base_smem + 8 * 8 + 4 * 32 * 4 + 64, 0, nullptr};
+        L.a.queries = d_a;
+        L.a.n = (uint32_t)n;
+        L.a.out = d_out;
+        L.a.error_flag = d_err;
+        L.a.stg_rows = plan.stg_rows;
+        L.a.stg_row_bytes = plan.stg_row_bytes;
+        L.a.tile_rows = plan.tile_rows;
+        L.grid = (unsigned)std::min<uint64_t>(n, (uint64_t)h->num_sms * 16);
+        if ((rc = DistDispatch::call(h->dev, L))) return rc;
+        GB_CUDA(cudaDeviceSynchronize());
+        int herr = 0;
+        GB_CUDA(cudaMemcpy(&herr, d_err, 4, cudaMemcpyDeviceToHost));
+        GB_CUDA(cudaMemcpy(out, d_out, (size_t)n * 4, cudaMemcpyDeviceToHost));
+        return error_from_bits(herr);
+    } catch (const std::exception& e) {
+        return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, std::string("exception: ") + e.what());
+    }
 }
 
 int granne_b200_reencode_index(const void* index_bytes, size_t index_len, void* out, size_t cap, size_t* out_len) {

@@ -235,6 +235,12 @@ void granne_b200_builder_free(granne_b200_builder* b);
 int granne_b200_elements_from_raw(int element_kind, const float* raw, uint64_t n, uint32_t dim, int device, void* out,
                                   size_t cap, size_t* out_len);
 
+/* compute_distance (py/src/lib.rs:71-89) for n pairs: out[i] = Vector::from(a_i).dist(&Vector::from(b_i)) for
+ * GRANNE_B200_ANGULAR (src/elements/angular.rs:55-74) or GRANNE_B200_ANGULAR_INT (angular_int.rs:19-59); `a`, `b` are
+ * n x dim raw f32 rows on the host.  A NaN distance (the reference panics) returns GRANNE_B200_ERR_NOT_FINITE. */
+int granne_b200_compute_distances(int element_kind, const float* a, const float* b, uint64_t n, uint32_t dim, int device,
+                                  float* out);
+
 /* Index::write_index (src/index/io.rs:11-70; py Granne.save_index, py/src/lib.rs:325-329) for a loaded or
  * builder-snapshot index: the granne index file image written from the staged rows.  out == NULL queries the size. */
 int granne_b200_write_index(const granne_b200_index* h, void* out, size_t cap, size_t* out_len);
