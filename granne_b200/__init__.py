@@ -10,6 +10,8 @@ from .api import (ANGULAR, ANGULAR_INT, EMBEDDINGS, QUERY_ELEMENT, QUERY_RAW_F32
                   apply_order, compute_distance, compute_distances, compute_keys_for_reordering, decode_layer, inspect_index, library_path,
                   load_library, merge_topk_device, order_by_keys, order_from_trails, reencode_index)
 
-__all__ = ["Granne", "GranneBuilder", "BuildConfig", "elements_from_raw", "GranneError", "ANGULAR", "ANGULAR_INT", "EMBEDDINGS", "QUERY_RAW_F32", "QUERY_ELEMENT",
+from .words import Embeddings, WordDict  # noqa: F401,E402
+
+__all__ = ["Embeddings", "WordDict", "Granne", "GranneBuilder", "BuildConfig", "elements_from_raw", "GranneError", "ANGULAR", "ANGULAR_INT", "EMBEDDINGS", "QUERY_RAW_F32", "QUERY_ELEMENT",
            "load_library", "library_path", "merge_topk_device", "inspect_index", "decode_layer", "reencode_index",
            "apply_order", "compute_distance", "compute_distances", "order_by_keys", "order_from_trails", "compute_keys_for_reordering"]

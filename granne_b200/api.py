@@ -112,8 +112,9 @@ class Granne:
     """granne.Granne (py/src/lib.rs:149-344) on the GPU.
 
     Granne(index_path, element_type, elements_path, embeddings_path=None, words_path=None, device=0)
-    element_type: "angular" | "angular_int" | "embeddings".  `words_path` is accepted for signature compatibility;
-    string queries (word lookup, py/src/variants/mod.rs:9-78) are outside the search path — pass vectors.
+    element_type: "angular" | "angular_int" | "embeddings".  With `words_path` an "embeddings" index also takes string
+    queries and reports elements as words (WordEmbeddingsGranne, py/src/variants/index.rs:41-139); the lookup and the
+    ordered row sum happen on the host, the search itself on the GPU.
     """
 
     def __init__(self, index_path, element_type, elements_path, embeddings_path=None, words_path=None, device=0):
@@ -129,6 +130,7 @@ class Granne:
         self.device = device
         self._elements_src = ("path", elements_path)
         self._embeddings_src = ("path", embeddings_path) if embeddings_path else None
+        self._words_path = words_path
 
     @classmethod
     def from_bytes(cls, index_bytes, element_type, elements_bytes, embeddings_bytes=None, device=0):
@@ -197,14 +199,21 @@ class Granne:
         emb = getattr(self, "_embeddings_src", None)
         emb_bytes = self._source_bytes(emb) if emb is not None else None
         fresh = Granne.from_bytes(new_index, kind, new_elements, emb_bytes, device=self.device)
+        fresh._words_path = getattr(self, "_words_path", None)
         self.close()
+        self._words = None
         self.__dict__.update(fresh.__dict__)
         fresh._h = None
         return [int(x) for x in order]
 
     def reorder(self, show_progress=False):
         """Granne.reorder(show_progress) (py/src/lib.rs:311-315, reorder.rs:59-82): reorders index and elements in
-        place for locality; returns the permutation (new -> old)."""
+        place for locality; returns the permutation (new -> old).  "embeddings" indexes are reordered by
+        compute_keys_for_reordering like the reference's Python class (py/src/variants/index.rs:70-75)."""
+        if self.element_kind == EMBEDDINGS:
+            keys = compute_keys_for_reordering(self._source_bytes(self._elements_src),
+                                               self._source_bytes(self._embeddings_src))
+            return self.reorder_by_keys(keys)
         return self._reopen_reordered(self.compute_order())
 
     def reorder_by_keys(self, keys, show_progress=False):
@@ -290,8 +299,33 @@ class Granne:
             return ids, dists, counts, stats
         return ids, dists, counts
 
+    def _word_tables(self):
+        """(WordDict, embeddings table, per-element id lists) for an "embeddings" index opened with words_path."""
+        if getattr(self, "_words", None) is None:
+            from . import words as W
+
+            if self.element_kind != EMBEDDINGS or getattr(self, "_words_path", None) is None:
+                raise ValueError("string queries need an \"embeddings\" index opened with words_path")
+            self._words = (W.WordDict(self._words_path), W.read_dense_f32(self._source_bytes(self._embeddings_src)),
+                           W.read_sum_terms(self._source_bytes(self._elements_src)))
+        return self._words
+
+    def get_internal_element(self, idx):
+        """Granne.get_internal_element(idx) (py/src/lib.rs:255-257): the words of an "embeddings" element
+        (py/src/variants/index.rs:133-138); the element itself for the vector types."""
+        if self.element_kind != EMBEDDINGS:
+            return self.get_element(idx)
+        words, _, terms = self._word_tables()
+        return words.get_words(terms[idx])
+
     def search(self, element, max_search=DEFAULT_MAX_SEARCH, num_elements=DEFAULT_NUM_ELEMENTS):
-        """Granne.search(element, max_search=200, num_elements=10) -> [(id, distance)] (py/src/lib.rs:227-233)."""
+        """Granne.search(element, max_search=200, num_elements=10) -> [(id, distance)] (py/src/lib.rs:227-233); a str
+        query is the sum of its words' embeddings (py/src/variants/index.rs:112-125)."""
+        if isinstance(element, str):
+            from . import words as W
+
+            words, table, _ = self._word_tables()
+            element = W.create_embedding(table, words.get_word_ids(element))
         ids, dists, counts = self.search_batch(np.asarray(element)[None, :], max_search, num_elements)
         return [(int(ids[0, i]), float(dists[0, i])) for i in range(int(counts[0]))]
 

@@ -51,3 +51,57 @@ def test_nan_is_an_error_like_the_reference_panic():
     assert ei.value.code == -6                                               # NotNan panic, angular.rs:70
     with pytest.raises(ValueError):
         granne_b200.compute_distance("embeddings", a[0], b[0])               # "Unsupported element type"
+
+
+def test_embeddings_class_distances(oracle, tmp_path):
+    # Embeddings.dist / dists (py/src/embeddings.rs:78-95): angular distance of the normalised sums
+    emb = random_vectors(60, 20, seed=9)
+    e = granne_b200.Embeddings()
+    for i, row in enumerate(emb):
+        e.append(row.tolist(), "w%d" % i)
+
+    def want(l, r):
+        a = oracle.normalize_f32(np.asarray(e.get_embedding(l), dtype=np.float32))
+        b = oracle.normalize_f32(np.asarray(e.get_embedding(r), dtype=np.float32))
+        return float(oracle.dist_f32(a, b))
+
+    assert e.dist("w1 w2 w3", [4, 5]) == want("w1 w2 w3", [4, 5])
+    rights = ["w7", [8, 9, 10], 11, "w1 w2 w3"]
+    assert e.dists("w1 w2 w3", rights) == [want("w1 w2 w3", r) for r in rights]
+    assert abs(e.dist(3, 3)) < 1e-5 and e.dists(0, []) == []
+
+
+def test_string_queries_on_an_embeddings_index(oracle, tmp_path):
+    # WordEmbeddingsGranne (py/src/variants/index.rs:41-139): str query -> word ids -> create_embedding -> search
+    from helpers.data import build_fixture
+
+    el, g, ib, eb, mb = build_fixture(oracle, "embeddings", 400, 16, seed=12, num_neighbors=10, max_search=30,
+                                      num_embeddings=90)
+    paths = {k: str(tmp_path / k) for k in ("index", "elements", "embeddings", "words")}
+    for k, data in (("index", ib), ("elements", eb), ("embeddings", mb)):
+        with open(paths[k], "wb") as f:
+            f.write(data)
+    d = granne_b200.WordDict()
+    for i in range(90):
+        d.push("tok%d" % i)
+    d.write(paths["words"])
+    index = granne_b200.Granne(paths["index"], "embeddings", paths["elements"], paths["embeddings"], paths["words"])
+    assert index.get_internal_element(5) == " ".join("tok%d" % t for t in el.terms(5))
+    query = "tok3 tok4 missing tok5"
+    vec = np.asarray(granne_b200.Embeddings(paths["embeddings"], paths["words"]).get_embedding(query), dtype=np.float32)
+    got = index.search(query, 30, 8)
+    assert got == index.search(vec, 30, 8)
+    ref = g.search_batch(vec[None, :], 30, 8)
+    assert [i for i, _ in got] == ref[0][0, :len(got)].tolist()
+    assert np.array_equal(np.array([x for _, x in got], dtype=np.float32).view(np.uint32), ref[1][0, :len(got)].view(np.uint32))
+    # element 3 = ids 3..7 (test_helper::random_sum_embeddings): its own words find it at distance ~0
+    own = index.search(index.get_internal_element(3), 30, 1)
+    assert own[0][0] == 3 and own[0][1] < 1e-5
+    # reorder for this type = reorder_by_keys(compute_keys_for_reordering) (py/src/variants/index.rs:70-75)
+    order = np.array(index.reorder())
+    keys = el.reorder_keys()
+    assert np.array_equal(order, g.order_by_keys(keys))
+    again = index.search(query, 30, 8)
+    assert [int(order[i]) for i, _ in again] == [i for i, _ in got]
+    assert index.get_internal_element(0) == " ".join("tok%d" % t for t in el.terms(int(order[0])))
+    index.close()
