@@ -69,6 +69,7 @@ def load_library():
         "granne_b200_apply_order": (i32, [vp, sz, i32, vp, sz, vp, u64, vp, sz, C.POINTER(sz), vp, sz, C.POINTER(sz)]),
         "granne_b200_build_config_default": (None, [vp]),
         "granne_b200_builder_new": (i32, [vp, i32, vp, sz, vp, sz, i32, C.POINTER(vp)]),
+        "granne_b200_builder_append": (i32, [vp, vp, sz]),
         "granne_b200_builder_build": (i32, [vp, u64]),
         "granne_b200_builder_len": (u64, [vp]),
         "granne_b200_builder_num_layers": (u64, [vp]),
@@ -429,11 +430,32 @@ class GranneBuilder:
                                          device, C.byref(h)))
         self._h = h
         self.device = device
+        self._element_type = element_type
         self._elements_bytes = elements_bytes
         self._embeddings_bytes = embeddings_bytes
+        self._pending = []
+
+    def append(self, element):
+        """GranneBuilder.append(element) (py/src/lib.rs:474-476; py/src/variants/builder.rs:6-21): the raw vector
+        becomes an element (`Vector::from`) and is pushed; it is indexed by the next build().  Rows are buffered and
+        handed to the library in one batch."""
+        if _kind(self._element_type) == EMBEDDINGS:
+            raise ValueError("append is implemented for the angular and angular_int containers")
+        self._pending.append(np.asarray(element, dtype=np.float32))
+
+    def _flush(self):
+        if not self._pending:
+            return
+        raw = np.stack(self._pending)
+        self._pending = []
+        image = elements_from_raw(self._element_type, raw, self.device)
+        _check(load_library().granne_b200_builder_append(self._h, _ptr(image), image.size))
+        old = np.frombuffer(self._elements_bytes, dtype=np.uint8)
+        self._elements_bytes = np.concatenate([old, image[8:]])  # same u64 width prefix, more rows
 
     def build(self, num_elements=0):
         """Builder::build() / build_partial(num_elements)."""
+        self._flush()
         _check(load_library().granne_b200_builder_build(self._h, int(num_elements)))
 
     def __len__(self):
@@ -461,6 +483,7 @@ class GranneBuilder:
 
     def get_index(self):
         """GranneBuilder::get_index: a searchable Granne sharing the staged elements."""
+        self._flush()
         h = C.c_void_p()
         _check(load_library().granne_b200_builder_get_index(self._h, C.byref(h)))
         g = Granne.__new__(Granne)
@@ -472,6 +495,7 @@ class GranneBuilder:
 
     def save_elements(self, path):
         """GranneBuilder.save_elements(path) (py/src/lib.rs:518-522)."""
+        self._flush()
         with open(path, "wb") as f:
             f.write(bytes(self._elements_bytes))
 
@@ -487,6 +511,7 @@ class GranneBuilder:
 
     def num_elements(self):
         """GranneBuilder.num_elements() (py/src/lib.rs:559-561): elements held, indexed or not."""
+        self._flush()
         return int(load_library().granne_b200_builder_num_elements(self._h))
 
     def close(self):

@@ -1166,6 +1166,72 @@ int granne_b200_builder_new(const granne_b200_build_config* cfg, int element_kin
     }
 }
 
+// GranneBuilder::push for the dense containers (ExtendableElementContainer::push, src/index/mod.rs:512-531;
+// src/elements/dense_vector.rs:120-136): `elements_bytes` is an elements file image of the same width whose rows are
+// appended to the staged container.  The appended elements are indexed by the next build() / build_partial().
+int granne_b200_builder_append(granne_b200_builder* b, const void* elements_bytes, size_t elements_len) {
+    if (!b || !elements_bytes) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "null argument");
+    try {
+        Handle* h = b->h.get();
+        gb::DeviceIndex& d = h->dev;
+        if (d.kind != gb::kAngularF32 && d.kind != gb::kAngularI8)
+            return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "append supports the angular and angular_int containers");
+        const bool i8 = d.kind == gb::kAngularI8;
+        const size_t esz = i8 ? 1 : 4;
+        gb::DenseView dv;
+        std::string err;
+        if (!gb::parse_dense(static_cast<const uint8_t*>(elements_bytes), elements_len, esz, &dv, &err))
+            return fail(GRANNE_B200_ERR_FORMAT, err);
+        if (dv.dim != d.dim) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "appended elements have a different width");
+        if (dv.num == 0) return GRANNE_B200_OK;
+        const uint64_t old_n = d.num_vectors, new_n = old_n + dv.num;
+        if (new_n >= 0xFFFFFFFFull) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "too many elements");  // :420
+        GB_CUDA(cudaSetDevice(h->device));
+        GB_CUDA(cudaStreamSynchronize(b->ws->stream));
+        const size_t row_bytes = (size_t)d.row_stride * esz;
+        uint8_t* dst = nullptr;
+        GB_CUDA(cudaMalloc(&dst, std::max<size_t>((size_t)new_n * row_bytes, 16)));
+        std::shared_ptr<void> owner(dst, [](void* q) { cudaFree(q); });
+        if (old_n) GB_CUDA(cudaMemcpy(dst, d.vectors, (size_t)old_n * row_bytes, cudaMemcpyDeviceToDevice));
+        // new rows: upload in slabs, then the same re-layout kernels as the loader
+        const uint64_t slab = std::max<uint64_t>(1, (64ull << 20) / ((size_t)d.dim * esz));
+        uint8_t* tmp = nullptr;
+        GB_CUDA(cudaMalloc(&tmp, (size_t)std::min<uint64_t>(slab, dv.num) * d.dim * esz));
+        std::shared_ptr<void> tmp_owner(tmp, [](void* q) { cudaFree(q); });
+        for (uint64_t r0 = 0; r0 < dv.num; r0 += slab) {
+            const uint64_t nr = std::min<uint64_t>(slab, dv.num - r0);
+            GB_CUDA(cudaMemcpy(tmp, dv.data + r0 * d.dim * esz, (size_t)nr * d.dim * esz, cudaMemcpyHostToDevice));
+            uint8_t* out_rows = dst + (size_t)(old_n + r0) * row_bytes;
+            if (i8)
+                gb::pad_rows_i8_kernel<<<h->num_sms * 8, 256>>>(reinterpret_cast<const int8_t*>(tmp),
+                                                                reinterpret_cast<int8_t*>(out_rows), nr, d.dim,
+                                                                d.row_stride);
+            else
+                gb::permute_rows_f32_kernel<<<h->num_sms * 8, 256>>>(reinterpret_cast<const float*>(tmp),
+                                                                     reinterpret_cast<float*>(out_rows), nr, d.dim,
+                                                                     d.full, d.vec_group, d.row_stride);
+            h->launches++;
+            GB_CUDA(cudaGetLastError());
+        }
+        GB_CUDA(cudaDeviceSynchronize());
+        // swap the container; snapshots handed out by get_index keep the old buffer alive through their own reference
+        for (auto it = h->allocations.begin(); it != h->allocations.end(); ++it)
+            if (it->get() == d.vectors) {
+                h->device_bytes -= std::min<uint64_t>(h->device_bytes, std::max<size_t>((size_t)old_n * row_bytes, 16));
+                h->allocations.erase(it);
+                break;
+            }
+        h->allocations.push_back(owner);
+        h->device_bytes += std::max<size_t>((size_t)new_n * row_bytes, 16);
+        d.vectors = dst;
+        d.num_vectors = new_n;
+        d.num_elements = new_n;
+        return GRANNE_B200_OK;
+    } catch (const std::exception& e) {
+        return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, std::string("exception: ") + e.what());
+    }
+}
+
 int granne_b200_builder_build(granne_b200_builder* b, uint64_t num_elements) {
     if (!b) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "builder is null");
     try {

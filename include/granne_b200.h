@@ -210,6 +210,10 @@ typedef struct granne_b200_builder granne_b200_builder;
 int granne_b200_builder_new(const granne_b200_build_config* cfg, int element_kind, const void* elements_bytes,
                             size_t elements_len, const void* embeddings_bytes, size_t embeddings_len, int device,
                             granne_b200_builder** out);
+/* GranneBuilder::push (src/index/mod.rs:512-531; py GranneBuilder.append, py/src/lib.rs:474-476) for the angular and
+ * angular_int containers: appends the rows of an elements file image (same width) to the builder's container; they are
+ * indexed by the next build.  Not concurrent with other calls on `b`. */
+int granne_b200_builder_append(granne_b200_builder* b, const void* elements_bytes, size_t elements_len);
 /* Builder::build_partial(num_elements) (:374-402); num_elements == 0 means Builder::build() (all elements, :366-368). */
 int granne_b200_builder_build(granne_b200_builder* b, uint64_t num_elements);
 uint64_t granne_b200_builder_len(const granne_b200_builder* b);        /* Index::len for the builder (:329-331) */

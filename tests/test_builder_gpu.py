@@ -173,3 +173,41 @@ def test_python_class_surface_save_and_reload(tmp_path, oracle):
     assert np.array_equal(want[0], got[0]) and np.array_equal(want[1].view(np.uint32), got[1].view(np.uint32))
     for h in (snap, index, b):
         h.close()
+
+
+@pytest.mark.parametrize("kind", ["angular", "angular_int"])
+def test_append_then_build_incrementally(oracle, kind):
+    # GranneBuilder.append (py/src/lib.rs:474-476 -> GranneBuilder::push, src/index/mod.rs:512-531): pushed elements are
+    # `Vector::from(raw)` and get indexed by the next build(); earlier snapshots keep their container
+    raw = random_vectors(1000, 24, seed=31)
+    whole = granne_b200.elements_from_raw(kind, raw).tobytes()
+    first = granne_b200.elements_from_raw(kind, raw[:600]).tobytes()
+    b = granne_b200.GranneBuilder(kind, first, num_neighbors=20, max_search=30)
+    b.build()
+    snap = b.get_index()
+    assert len(b) == 600 and b.num_elements() == 600
+    for row in raw[600:]:
+        b.append(row.tolist())
+    assert b.num_elements() == 1000 and len(b) == 600            # pushed, not yet indexed
+    b.build(800)
+    assert len(b) == 800
+    b.build()
+    assert len(b) == 1000 and len(snap) == 600 and snap.num_elements() == 600
+    index = b.get_index()
+    rows = oracle.Elements.from_bytes(kind, whole).rows()
+    for i in (0, 599, 600, 777, 999):
+        assert np.array_equal(index.get_element(i), rows[i])
+    assert _self_recall(index, rows, 30) > 0.95
+    assert _self_recall(snap, rows[:600], 30) > 0.95
+    assert bytes(index.elements_bytes()) == whole
+    # the index over the appended container is a valid granne index: the oracle searches it identically
+    g = oracle.Granne.from_bytes(index.index_bytes(), oracle.Elements.from_bytes(kind, whole))
+    q = random_vectors(64, 24, seed=32)
+    ref = g.search_batch(q, 40, 10, with_stats=True)
+    got = index.search_batch(q, 40, 10, with_stats=True)
+    assert np.array_equal(ref[0], got[0]) and np.array_equal(ref[1].view(np.uint32), got[1].view(np.uint32))
+    with pytest.raises(granne_b200.GranneError):
+        b._pending.append(np.zeros(7, dtype=np.float32))           # wrong width is rejected by the library
+        b._flush()
+    for h in (snap, index, b):
+        h.close()
