@@ -10,7 +10,11 @@
 // for this path (tests/test_oracle_kat.py): layer sizes (src/index/tests.rs:305-335), delta coding
 // (src/slice_vector/set_vector.rs:231-248), the raw-vs-vbyte size rule (set_vector.rs:275-283), odd-byte ints
 // (src/odd_byte_int.rs:43-79), dot/sum/dist tolerances (src/math.rs:166-196, src/elements/angular.rs:97-126),
-// self-recall > 0.95 (src/index/tests.rs:41-62,114-132) and format round-trips (src/index/tests.rs:337-451).
+// self-recall > 0.95 (src/index/tests.rs:41-62,114-132) and format round-trips (src/index/tests.rs:337-451);
+// tests/test_oracle_formats_kat.py adds Offsets (src/slice_vector/offsets.rs:302-351), the MultiSetVector writers
+// (set_vector.rs:318-425), the variable-width element container, select_neighbors / empty_build / write_and_load /
+// incremental builds (src/index/tests.rs:11-40,134-242,292-417); tests/test_oracle_reorder.py the reorder and
+// permute tests (src/index/reorder.rs:294-334, src/slice_vector/mod.rs:1028-1092, embeddings/reorder.rs:60-102).
 // Byte-level parity of the stream-vbyte coding (third-party crate stream-vbyte 0.3.2, Cargo.toml:42, not vendored
 // under /root/reference) is restated from the published Stream VByte layout and is otherwise UNPINNED.
 //
@@ -359,35 +363,47 @@ struct CompressedLayer {  // MultiSetVector over a borrowed byte range
 };
 
 // write_as_multi_set_vector (set_vector.rs:169-221) + Offsets::push (offsets.rs:233-241)
+// Offsets::new / push (offsets.rs:225-241) over Chunk::new / push (offsets.rs:158-204): chunks of 60 u16 deltas with
+// a u64 `initial`; unused deltas are 0xFFFF; the first chunk starts with initial = 0.  `ok` turns false where the
+// reference panics (offset below the previous one, offsets.rs:201; delta above u16::MAX, offsets.rs:203).
+struct OffsetsWriter {
+    std::vector<u8> chunks;
+    size_t cur_len = 0;
+    u64 last_offset = 0;  // Chunk::last() of the current chunk, or its `initial` while it is empty
+    bool ok = true;
+
+    OffsetsWriter() { new_chunk(0); }
+    void new_chunk(u64 initial) {
+        chunks.resize(chunks.size() + CHUNK_BYTES, 0xFF);
+        write_uint_le(&chunks[chunks.size() - CHUNK_BYTES], initial, 8);
+        cur_len = 0;
+        last_offset = initial;
+    }
+    void push(u64 offset) {
+        if (cur_len == OFFSETS_PER_CHUNK) new_chunk(offset);  // is_full -> Chunk::new(offset), then push(offset)
+        if (offset < last_offset) {
+            ok = false;
+            return;
+        }
+        const u64 delta = offset - last_offset;
+        if (delta > 0xFFFF) {
+            ok = false;
+            return;
+        }
+        write_uint_le(&chunks[chunks.size() - CHUNK_BYTES + 8 + 2 * cur_len], delta, 2);
+        ++cur_len;
+        last_offset = offset;
+    }
+};
+
 void write_layer_blob(const std::vector<std::vector<u32>>& lists, std::vector<u8>& out) {
     size_t n = lists.size();
     size_t bytes_for_offsets = (1 + n / OFFSETS_PER_CHUNK) * CHUNK_BYTES;
     size_t base = out.size();
     out.resize(base + 8 + bytes_for_offsets, 0);
     write_uint_le(&out[base], bytes_for_offsets, 8);
-    // chunks
-    std::vector<u8> chunkbuf(bytes_for_offsets, 0xFF);
-    size_t num_chunks = bytes_for_offsets / CHUNK_BYTES;
-    for (size_t c = 0; c < num_chunks; ++c) write_uint_le(&chunkbuf[c * CHUNK_BYTES], 0, 8);
-    size_t cur_chunk = 0, cur_len = 0;
-    u64 last_offset = 0;
-    auto push_offset = [&](u64 offset) {
-        if (cur_len == OFFSETS_PER_CHUNK) {  // chunk full -> new chunk with initial = offset, then push(offset)
-            ++cur_chunk;
-            cur_len = 0;
-            write_uint_le(&chunkbuf[cur_chunk * CHUNK_BYTES], offset, 8);
-            last_offset = offset;
-        }
-        u64 delta = offset - last_offset;
-        if (delta > 0xFFFF) {
-            std::fprintf(stderr, "oracle: offset delta too large\n");
-            std::abort();
-        }
-        write_uint_le(&chunkbuf[cur_chunk * CHUNK_BYTES + 8 + 2 * cur_len], delta, 2);
-        ++cur_len;
-        last_offset = offset;
-    };
-    push_offset(0);
+    OffsetsWriter offsets;
+    offsets.push(0);
     std::vector<u8> enc;
     u64 total = 0;
     for (size_t i = 0; i < n; ++i) {
@@ -396,13 +412,13 @@ void write_layer_blob(const std::vector<std::vector<u32>>& lists, std::vector<u8
         set_encode(s, enc);
         out.insert(out.end(), enc.begin(), enc.end());
         total += enc.size();
-        push_offset(total);
+        offsets.push(total);
     }
-    if (cur_chunk + 1 != num_chunks) {
-        std::fprintf(stderr, "oracle: chunk count mismatch\n");
+    if (!offsets.ok || offsets.chunks.size() != bytes_for_offsets) {
+        std::fprintf(stderr, "oracle: offsets do not fit (delta too large or chunk count mismatch)\n");
         std::abort();
     }
-    std::memcpy(&out[base + 8], chunkbuf.data(), bytes_for_offsets);
+    std::memcpy(&out[base + 8], offsets.chunks.data(), bytes_for_offsets);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1395,5 +1411,110 @@ void orc_elements_permute(void* elements, const uint64_t* order, uint64_t n) {
     permute_elements((Elements*)elements, std::vector<u64>(order, order + n));
 }
 void orc_sum_reorder_keys(void* elements, uint64_t* keys_out) { embedding_reorder_keys(*(Elements*)elements, keys_out); }
+
+// ---- format KAT hooks ----
+// Offsets: push every offset, then read them back through the reader (offsets.rs:245-270).  Returns the number of
+// offsets the reader reports, or -1 where the reference panics (offsets.rs:158-160,223).
+int64_t orc_offsets_roundtrip(const uint64_t* offsets, uint64_t n, uint64_t* out, uint64_t* last_out) {
+    OffsetsWriter w;
+    for (uint64_t i = 0; i < n; ++i) {
+        w.push(offsets[i]);
+        if (!w.ok) return -1;
+        if (last_out) last_out[i] = w.last_offset;  // Offsets::last (offsets.rs:261-265)
+    }
+    CompressedLayer r;
+    r.chunks = w.chunks.data();
+    r.num_chunks = w.chunks.size() / CHUNK_BYTES;
+    // Offsets::len (offsets.rs:267-270)
+    size_t len = 0;
+    if (r.num_chunks) {
+        const u8* last = r.chunks + (r.num_chunks - 1) * CHUNK_BYTES;
+        size_t l = 0;
+        while (l < OFFSETS_PER_CHUNK && CompressedLayer::chunk_delta(last, l) != DELTA_UNUSED) ++l;
+        len = OFFSETS_PER_CHUNK * (r.num_chunks - 1) + l;
+    }
+    for (size_t i = 0; i < len && i < n; ++i) out[i] = r.offset_get(i);
+    return (int64_t)len;
+}
+// MultiSetVector blob from lists (write_as_multi_set_vector, set_vector.rs:169-221, with the predicate already applied
+// by the caller); lists are given flattened with their lengths.
+uint64_t orc_multiset_blob(const uint32_t* flat, const uint64_t* lens, uint64_t n, uint8_t* out, uint64_t cap) {
+    std::vector<std::vector<u32>> lists(n);
+    size_t pos = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        lists[i].assign(flat + pos, flat + pos + lens[i]);
+        pos += lens[i];
+    }
+    std::vector<u8> blob;
+    write_layer_blob(lists, blob);
+    if (out == nullptr) return blob.size();
+    if (blob.size() > cap) return 0;
+    std::memcpy(out, blob.data(), blob.size());
+    return blob.size();
+}
+// MultiSetVector::from_bytes(...).len() / .get(idx) (set_vector.rs:57-69, offsets.rs:127-139)
+int64_t orc_multiset_len(const uint8_t* blob, uint64_t len) {
+    CompressedLayer L;
+    if (!L.load(blob, len)) return -1;
+    return (int64_t)L.n;
+}
+uint64_t orc_multiset_get(const uint8_t* blob, uint64_t len, uint64_t idx, uint32_t* out, uint64_t cap) {
+    CompressedLayer L;
+    if (!L.load(blob, len) || idx >= L.n) return ~0ull;
+    std::vector<u32> v;
+    L.get(idx, v);
+    for (size_t i = 0; i < v.size() && i < cap; ++i) out[i] = v[i];
+    return v.size();
+}
+
+// GranneBuilder::select_neighbors (index/mod.rs:849-883) over `elements`; candidates ascending by distance.
+uint64_t orc_select_neighbors(void* elements, const uint64_t* cand_ids, const float* cand_dists, uint64_t n,
+                              uint64_t max_neighbors, uint64_t* out_ids, float* out_dists) {
+    Builder b;
+    b.elements = (Elements*)elements;
+    std::vector<Builder::Cand> c(n);
+    for (uint64_t i = 0; i < n; ++i) c[i] = {cand_ids[i], cand_dists[i]};
+    auto r = b.select_neighbors(c, max_neighbors);
+    for (size_t i = 0; i < r.size(); ++i) {
+        out_ids[i] = r[i].first;
+        out_dists[i] = r[i].second;
+    }
+    return r.size();
+}
+
+// Stateful builder (GranneBuilder::new / build_partial / get_index, index/mod.rs:303-315,374-402,483-488): successive
+// build_partial calls continue from the layers built so far, like the reference's incremental_build tests.
+void* orc_builder_new(void* elements, uint64_t num_neighbors, uint64_t max_search, float layer_multiplier, int reinsert,
+                      int64_t expected_num_elements) {
+    auto* b = new Builder();
+    b->elements = (Elements*)elements;
+    b->config.num_neighbors = num_neighbors;
+    b->config.max_search = max_search;
+    b->config.layer_multiplier = layer_multiplier;
+    b->config.reinsert_elements = reinsert != 0;
+    b->config.expected_num_elements = expected_num_elements;
+    b->ix.use_fixed = true;
+    b->ix.width = num_neighbors;
+    return b;
+}
+void orc_builder_free(void* p) { delete (Builder*)p; }
+// build_partial(num_elements) exactly (0 indexes nothing); returns 1 where the reference panics
+// ("Cannot index fewer elements than already in index", :379-382).
+int orc_builder_build_partial(void* p, uint64_t num_elements, int threads) {
+    auto* b = (Builder*)p;
+    if (num_elements < b->ix.len()) {
+        g_err = "Cannot index fewer elements than already in index.";
+        return 1;
+    }
+    b->build_partial(std::min<size_t>(num_elements, b->elements->len()), threads);
+    return 0;
+}
+void* orc_builder_get_index(void* p) {  // a copy of the layers built so far
+    auto* b = (Builder*)p;
+    auto* ix = new Index(b->ix);
+    ix->use_fixed = true;
+    if (ix->width == 0) ix->width = b->config.num_neighbors;
+    return ix;
+}
 
 }  // extern "C"

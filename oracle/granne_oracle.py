@@ -77,6 +77,15 @@ def lib():
         "orc_index_num_layers": (u64, [vp]),
         "orc_index_layer_len": (u64, [vp, u64]),
         "orc_index_get_neighbors": (u64, [vp, u64, u64, vp, u64]),
+        "orc_offsets_roundtrip": (i64, [vp, u64, vp, vp]),
+        "orc_multiset_blob": (u64, [vp, vp, u64, vp, u64]),
+        "orc_multiset_len": (i64, [vp, u64]),
+        "orc_multiset_get": (u64, [vp, u64, u64, vp, u64]),
+        "orc_select_neighbors": (u64, [vp, vp, vp, u64, u64, vp, vp]),
+        "orc_builder_new": (vp, [vp, u64, u64, f32, i32, i64]),
+        "orc_builder_free": (None, [vp]),
+        "orc_builder_build_partial": (i32, [vp, u64, i32]),
+        "orc_builder_get_index": (vp, [vp]),
         "orc_entrypoint_trail": (None, [vp, vp, u64, u64, vp]),
         "orc_compute_order": (None, [vp, vp, vp, i32]),
         "orc_order_by_keys": (None, [vp, vp, u64, vp]),
@@ -178,6 +187,52 @@ def delta_encode(ids):
     a = np.ascontiguousarray(ids, dtype=np.uint32).copy()
     lib().orc_delta_encode(_ptr(a), a.size)
     return a.tolist()
+
+
+def offsets_roundtrip(offsets):
+    """Offsets::push for every value, then Offsets::len / get / last (offsets.rs:225-270).  Returns
+    (len, values read back, last() after each push), or None where the reference panics."""
+    a = np.ascontiguousarray(offsets, dtype=np.uint64)
+    out = np.zeros(a.size, dtype=np.uint64)
+    last = np.zeros(a.size, dtype=np.uint64)
+    n = int(lib().orc_offsets_roundtrip(_ptr(a), a.size, _ptr(out), _ptr(last)))
+    if n < 0:
+        return None
+    return n, out[:n].tolist(), last.tolist()
+
+
+class MultiSetVector:
+    """MultiSetVector written by write_as_multi_set_vector (set_vector.rs:169-221) and loaded with from_bytes."""
+
+    def __init__(self, lists):
+        flat = np.ascontiguousarray([v for l in lists for v in l], dtype=np.uint32)
+        lens = np.ascontiguousarray([len(l) for l in lists], dtype=np.uint64)
+        if flat.size == 0:
+            flat = np.zeros(1, dtype=np.uint32)
+        if lens.size == 0:
+            lens = np.zeros(1, dtype=np.uint64)
+        n = lib().orc_multiset_blob(_ptr(flat), _ptr(lens), len(lists), None, 0)
+        self.blob = np.zeros(n, dtype=np.uint8)
+        lib().orc_multiset_blob(_ptr(flat), _ptr(lens), len(lists), _ptr(self.blob), n)
+
+    def __len__(self):
+        return int(lib().orc_multiset_len(_ptr(self.blob), self.blob.size))
+
+    def get(self, idx):
+        out = np.zeros(300, dtype=np.uint32)
+        n = int(lib().orc_multiset_get(_ptr(self.blob), self.blob.size, idx, _ptr(out), out.size))
+        return out[:n].tolist()
+
+
+def select_neighbors(elements, candidates, max_neighbors):
+    """GranneBuilder::select_neighbors (index/mod.rs:849-883); candidates = [(id, dist)] ascending by distance."""
+    ids = np.ascontiguousarray([c[0] for c in candidates], dtype=np.uint64)
+    ds = np.ascontiguousarray([c[1] for c in candidates], dtype=np.float32)
+    oi = np.zeros(max(1, len(candidates)), dtype=np.uint64)
+    od = np.zeros(max(1, len(candidates)), dtype=np.float32)
+    n = int(lib().orc_select_neighbors(elements._h, _ptr(ids), _ptr(ds), len(candidates), max_neighbors, _ptr(oi),
+                                       _ptr(od)))
+    return [(int(oi[i]), float(od[i])) for i in range(n)]
 
 
 # ---- element containers ------------------------------------------------------------------------------------------
@@ -423,3 +478,21 @@ class GranneBuilder:
         m, ef, mult, re, exp = self.cfg
         h = lib().orc_build(self.elements._h, m, ef, mult, int(re), exp, num_elements, threads)
         return Granne(h, self.elements)
+
+    # stateful use, like the reference's builder: build_partial(n) continues from what is already indexed
+    def build_partial(self, num_elements, threads=1):
+        """Builder::build_partial (index/mod.rs:374-402); returns the index built so far (get_index)."""
+        if getattr(self, "_b", None) is None:
+            m, ef, mult, re, exp = self.cfg
+            self._b = lib().orc_builder_new(self.elements._h, m, ef, mult, int(re), exp)
+        if lib().orc_builder_build_partial(self._b, num_elements, threads) != 0:
+            raise ValueError(lib().orc_last_error().decode())
+        return Granne(lib().orc_builder_get_index(self._b), self.elements)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_b", None):
+                lib().orc_builder_free(self._b)
+                self._b = None
+        except Exception:  # interpreter shutdown
+            pass
