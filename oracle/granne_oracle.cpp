@@ -1517,4 +1517,24 @@ void* orc_builder_get_index(void* p) {  // a copy of the layers built so far
     return ix;
 }
 
+// GranneBuilder::from_bytes (index/mod.rs:428-457): a builder that continues from an already built index; every
+// neighbour list is resized to the new config's num_neighbors (longer lists are truncated, :447).
+void* orc_builder_from_index(void* index, void* elements, uint64_t num_neighbors, uint64_t max_search,
+                             float layer_multiplier, int reinsert, int64_t expected_num_elements) {
+    auto* b = (Builder*)orc_builder_new(elements, num_neighbors, max_search, layer_multiplier, reinsert,
+                                        expected_num_elements);
+    auto* src = (Index*)index;
+    std::vector<u32> tmp;
+    for (size_t l = 0; l < src->num_layers(); ++l) {
+        std::vector<u32> rows(src->layer_len(l) * num_neighbors, UNUSED);
+        for (size_t i = 0; i < src->layer_len(l); ++i) {
+            src->get_neighbors(l, i, tmp);
+            tmp.resize(num_neighbors, UNUSED);
+            std::copy(tmp.begin(), tmp.end(), rows.begin() + i * num_neighbors);
+        }
+        b->ix.fixed.push_back(std::move(rows));
+    }
+    return b;
+}
+
 }  // extern "C"

@@ -84,6 +84,7 @@ def lib():
         "orc_select_neighbors": (u64, [vp, vp, vp, u64, u64, vp, vp]),
         "orc_builder_new": (vp, [vp, u64, u64, f32, i32, i64]),
         "orc_builder_free": (None, [vp]),
+        "orc_builder_from_index": (vp, [vp, vp, u64, u64, f32, i32, i64]),
         "orc_builder_build_partial": (i32, [vp, u64, i32]),
         "orc_builder_get_index": (vp, [vp]),
         "orc_entrypoint_trail": (None, [vp, vp, u64, u64, vp]),
@@ -318,6 +319,12 @@ class Elements:
         q = _f32(raw_query)
         return np.float32(lib().orc_elements_dist_to(self._h, idx, _ptr(q), int(already_element)))
 
+    def push(self, raw, as_is=False):
+        """ExtendableElementContainer::push for the vector containers: rows of raw f32 become elements
+        (`Vector::from`: normalised / quantised) and are appended (dense_vector.rs:120-136)."""
+        raw = _f32(np.atleast_2d(raw))
+        lib().orc_elements_push_f32(self._h, _ptr(raw), raw.shape[0], int(as_is))
+
     def terms(self, idx):
         """SumEmbeddings::get_terms (embeddings/mod.rs:106-108)."""
         out = np.zeros(256, dtype=np.uint32)
@@ -478,6 +485,14 @@ class GranneBuilder:
         m, ef, mult, re, exp = self.cfg
         h = lib().orc_build(self.elements._h, m, ef, mult, int(re), exp, num_elements, threads)
         return Granne(h, self.elements)
+
+    @classmethod
+    def from_index(cls, index, elements, **config):
+        """GranneBuilder::from_bytes (index/mod.rs:428-457): continue building from `index` with a new config."""
+        b = cls(elements, **config)
+        m, ef, mult, re, exp = b.cfg
+        b._b = lib().orc_builder_from_index(index._h, elements._h, m, ef, mult, int(re), exp)
+        return b
 
     # stateful use, like the reference's builder: build_partial(n) continues from what is already indexed
     def build_partial(self, num_elements, threads=1):

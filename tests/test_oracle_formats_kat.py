@@ -145,3 +145,56 @@ def test_incremental_build_with_write_and_read(oracle):
     # a one-shot build of the same elements has the same shape
     one = oracle.GranneBuilder(el, num_neighbors=20, max_search=20).build()
     assert [one.layer_len(l) for l in range(one.num_layers())] == [g.layer_len(l) for l in range(g.num_layers())]
+
+
+def _findable(g, element, idx, max_search):
+    return any(i == idx for i, _ in g.search(element, max_search, 1))
+
+
+def test_append_elements(oracle):
+    # append_elements (tests.rs:503-567): push 500, build, push 500 more, build; expected_num_elements(1000),
+    # layer_multiplier(10), num_neighbors(20), max_search(50) -> three layers both times
+    first, second = random_vectors(500, 50, seed=8), random_vectors(500, 50, seed=9)
+    el = oracle.Elements("angular", 50)
+    b = oracle.GranneBuilder(el, num_neighbors=20, max_search=50, layer_multiplier=10.0, expected_num_elements=1000)
+    el.push(first)
+    g = b.build_partial(len(el))
+    assert g.num_layers() == 3 and g.layer_len(2) == 500
+    assert _findable(g, first[123], 123, 50)
+    el.push(second)
+    g = b.build_partial(len(el))
+    assert g.num_layers() == 3 and g.layer_len(2) == 1000
+    assert _findable(g, first[123], 123, 50) and _findable(g, second[123], 500 + 123, 50)
+
+
+def test_with_elements_and_add_and_borrowed(oracle):
+    # with_borrowed_elements / with_elements_and_add (tests.rs:64-112): verify_search(index, 0.95, 40)
+    raw = random_vectors(600, 25, seed=10)
+    el = oracle.Elements.angular(raw[:500])
+    g = oracle.GranneBuilder(el, max_search=5, reinsert_elements=False).build()
+    rows = el.rows()
+    assert len(g) == 500
+    assert (g.search_batch(rows, 40, 1, already_element=True)[0][:, 0] == np.arange(500)).mean() > 0.95
+    b = oracle.GranneBuilder(el, num_neighbors=20, max_search=5, expected_num_elements=600)
+    el.push(raw[500:])
+    assert len(el) == 600
+    g = b.build_partial(600)
+    rows = el.rows()
+    assert (g.search_batch(rows, 40, 1, already_element=True)[0][:, 0] == np.arange(600)).mean() > 0.95
+
+
+def test_read_index_reduce_num_neighbors(oracle):
+    # read_index_reduce_num_neighbors (tests.rs:243-290): build half with num_neighbors 20, reload the file into a
+    # builder with num_neighbors 5, finish the build
+    el = oracle.Elements.angular(random_vectors(1000, 5, seed=11))
+    half = oracle.GranneBuilder(el, num_neighbors=20, max_search=10).build_partial(500)
+    assert len(half.get_neighbors(0)) > 5                             # "not necessarily true, but should be valid"
+    loaded = oracle.Granne.from_bytes(half.to_bytes(), el)
+    b = oracle.GranneBuilder.from_index(loaded, el, num_neighbors=5, max_search=10)
+    g = b.build_partial(500)
+    assert len(g) == 500 and g.num_layers() == half.num_layers()
+    g = b.build_partial(1000)
+    assert len(g) == 1000 and len(g.get_neighbors(0)) <= 5
+    for layer in range(g.num_layers()):
+        for i in range(0, g.layer_len(layer), 41):
+            assert len(g.get_neighbors(i, layer)) <= 5
