@@ -28,7 +28,7 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     granne_b200.load_library()
-    q = random_vectors(1000, 32, seed=77)  # not divisible by 8 ranks on purpose
+    q = random_vectors(1000, 32, seed=77)
     tq = torch.from_numpy(q).to(dev)
 
     # mode 1: replicated index (deterministic oracle build -> identical file image on every rank)
