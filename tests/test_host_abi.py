@@ -171,3 +171,24 @@ int main(void) {
                            str(src), "-o", exe, "-L" + libdir, "-lgranne_b200", "-Wl,-rpath," + libdir])
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and r.stdout.strip() == "ok", (r.returncode, r.stdout, r.stderr)
+
+
+def test_rust_shim_declarations_match_the_header():
+    # bindings/rust cannot be compiled here (no rustc): keep its extern block in sync with the C header mechanically
+    header = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "granne_b200.h")).read(), flags=re.S)
+    shim = open(os.path.join(ROOT, "bindings", "rust", "src", "lib.rs")).read()
+    extern = shim[shim.index('extern "C" {'):shim.index("pub const ANGULAR")]
+    decls = re.findall(r"fn (granne_b200_\w+)\s*\((.*?)\)\s*(?:->\s*[\w:\* ]+)?;", extern, flags=re.S)
+    assert len(decls) >= 20
+
+    def arity(params):
+        params = params.strip()
+        return 0 if params in ("", "void") else params.count(",") + 1
+
+    for name, params in decls:
+        m = re.search(r"\b%s\s*\((.*?)\)\s*;" % name, header, flags=re.S)
+        assert m, name + " is not declared in granne_b200.h"
+        rust_params = params.strip().rstrip(",")
+        assert arity(rust_params) == arity(m.group(1)), name
+    for used in set(re.findall(r"\b(granne_b200_\w+)\(", shim)):
+        assert any(used == d[0] for d in decls), used + " is called but not declared in the extern block"
