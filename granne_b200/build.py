@@ -9,8 +9,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SRC = os.path.join(HERE, "csrc", "granne_b200.cu")
-DEPS = [SRC, os.path.join(HERE, "csrc", "search_kernels.cuh"), os.path.join(HERE, "csrc", "formats.hpp"),
-        os.path.join(ROOT, "include", "granne_b200.h")]
+DEPS = sorted(os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HERE, "csrc"))) + [
+    os.path.join(ROOT, "include", "granne_b200.h")]
 LIB = os.path.join(HERE, "libgranne_b200.so")
 
 NVCC_FLAGS = [
@@ -40,6 +40,16 @@ def build(force=False, verbose=False):
     cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, SRC]
     subprocess.check_call(cmd)
     return LIB
+
+
+def build_variant(tag, defines=(), extra_flags=()):
+    """Experimental build next to the default library: libgranne_b200_<tag>.so with extra -D defines (e.g.
+    GB_MIN_BLOCKS=28) — select it at run time with GRANNE_B200_LIB=<path> (tools/ab_bench.py compares variants)."""
+    out = os.path.join(HERE, "libgranne_b200_%s.so" % tag)
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + ["-D%s" % d for d in defines] + list(extra_flags) + ["-o", out, SRC]
+    subprocess.check_call(cmd)
+    return out
 
 
 if __name__ == "__main__":
