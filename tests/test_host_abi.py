@@ -192,3 +192,40 @@ def test_rust_shim_declarations_match_the_header():
         assert arity(rust_params) == arity(m.group(1)), name
     for used in set(re.findall(r"\b(granne_b200_\w+)\(", shim)):
         assert any(used == d[0] for d in decls), used + " is called but not declared in the extern block"
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_graphs_decode_and_reencode_like_the_oracle(lib, oracle, seed):
+    # differential check on random adjacency lists: empty / short / long lists, small and large id gaps (raw-vs-vbyte
+    # rule, set_vector.rs:130-141), layer sizes around the 60-offsets-per-chunk boundary (offsets.rs:7)
+    from helpers.data import index_from_lists
+
+    rng = np.random.default_rng(seed)
+    sizes = sorted(int(x) for x in rng.choice([1, 2, 59, 60, 61, 119, 120, 121, 500, 3000], size=rng.integers(1, 4),
+                                              replace=False))
+    n_last = sizes[-1]
+    layers = []
+    for n in sizes:
+        lists = []
+        for _ in range(n):
+            deg = int(rng.choice([0, 1, 2, 3, 4, 5, 15, 30, 40], p=[.1, .1, .1, .1, .1, .1, .2, .15, .05]))
+            deg = min(deg, n)
+            if rng.random() < 0.3:  # clustered ids: small deltas compress well
+                start = int(rng.integers(0, max(1, n - deg + 1)))
+                ids = list(range(start, start + deg))
+            else:
+                ids = rng.choice(n, size=deg, replace=False).tolist()
+            lists.append(ids)
+        layers.append(lists)
+    image = index_from_lists(oracle, layers)
+    g = oracle.Granne.from_bytes(image, oracle.Elements.angular(np.ones((n_last, 2), dtype=np.float32)))
+    shape = api.inspect_index(image)
+    assert [s[0] for s in shape] == sizes
+    for l, lists in enumerate(layers):
+        rows = api.decode_layer(image, l)
+        assert shape[l][1] == max((len(x) for x in lists), default=0)
+        for i in range(0, sizes[l], max(1, sizes[l] // 200)):
+            want = sorted(lists[i])
+            assert g.get_neighbors(i, l) == want
+            assert rows[i, :len(want)].tolist() == want and (rows[i, len(want):] == 0xFFFFFFFF).all()
+    assert api.reencode_index(image) == image == g.to_bytes()
