@@ -191,7 +191,7 @@ __device__ __forceinline__ void setup_ctx(const DeviceIndex& ix, WarpCtx& c, Lin
         c.stg = sp;
         sp += (size_t)stg_rows * stg_row_bytes;
     }
-    if (Dist::kStaged) {
+    if (Dist::kMbar) {
         if (c.lane == 0) mbar_init(c.bar, 1);
         __syncwarp();
     }

@@ -51,7 +51,7 @@ constexpr unsigned long long kFlagExpanded = 1ull << 63;
 constexpr unsigned long long kKeyMask = ~kFlagExpanded;
 constexpr unsigned kFullMask = 0xFFFFFFFFu;
 constexpr int kTileStride = 36;  // floats per tile row: 16-byte aligned rows, conflict-free LDS.128 per quarter warp
-constexpr int kIdScratchBytes = 128;  // 32 x u32 scratch for compacting candidate ids
+constexpr int kIdScratchBytes = 384;  // 32 x u32 compacted candidate ids + 32 x (id, distance bits) keys of a merge
 __host__ __device__ constexpr uint32_t tile_bytes_for_rows(uint32_t rows) { return rows * kTileStride * 4u + kIdScratchBytes; }
 
 enum ElementKind : int { kAngularF32 = 0, kAngularI8 = 1, kSumEmbeddings = 2 };
@@ -236,6 +236,22 @@ __device__ __forceinline__ unsigned long long make_policy_evict_last() {
     return p;
 }
 
+// ---- per-lane asynchronous copies (cp.async -> LDGSTS): global -> shared without staging registers ----------------
+// Lane l copies (and later reads back) only ITS OWN bytes of a row, so completion needs no cross-lane barrier: the
+// issuing thread waits for its own copies with cp.async.wait_all.  One instruction copies 32 x BYTES contiguous bytes.
+template <int BYTES>
+__device__ __forceinline__ void cp_async_lane(uint32_t dst, const void* src) {
+    // (no L2::cache_hint operand: ptxas 12.9 encodes LDGSTS + policy with never-written uniform registers in this
+    // kernel and the instruction traps as illegal on sm_100a)
+    if (BYTES == 16)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    else if (BYTES == 8)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+    else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // Strictly ordered sum of the 32 lane partials of ONE value (used where only a single candidate is live):
 // r = 0; for i in 0..32 { r += chunk[i] }   (src/math.rs:27-30).  All lanes return the same r.
 __device__ __forceinline__ float ordered_lane_sum_bcast(float p) {
@@ -259,7 +275,8 @@ struct DistF32 {
     static constexpr int V = (FULL % 4 == 0) ? 4 : ((FULL % 2 == 0) ? 2 : 1);
     static constexpr int G = FULL / V;
     static constexpr int NQ = FULL > 0 ? FULL : 1;
-    static constexpr bool kStaged = FULL > 0;
+    static constexpr bool kStaged = FULL > 0;  // candidate rows pass through the shared staging tile
+    static constexpr bool kMbar = false;        // ... with cp.async groups, not an mbarrier
     float q[NQ];
 
     __device__ __forceinline__ void load_query(const DeviceIndex& ix, const WarpCtx& c) {
@@ -315,39 +332,52 @@ struct DistF32 {
     }
 
     // Batches of up to stg_rows (<= 8 = tile rows) candidates: gather, lane partials into the tile, ordered sums.
+    // Gather: one cp.async per row (per 32-chunk group): lane l copies the V*4 bytes of the permuted row that lane l
+    // itself consumes, so a row costs SHFL + address + LDGSTS, all rows of the batch are in flight together, no data
+    // registers are held and no cross-lane barrier is needed before the partial sums.
     __device__ __forceinline__ float dists(const DeviceIndex& ix, WarpCtx& c, uint32_t my_id, int k) {
         float d = 0.0f;
         if (FULL > 0) {
             const uint32_t stride_bytes = ix.row_stride * 4u;
-            const uint32_t copy_bytes = FULL * 128u;  // the permuted chunk part of a row (multiple of 16)
+            constexpr uint32_t row_bytes = FULL * 128u;  // the permuted chunk part of a row
+            constexpr uint32_t lane_bytes = V * 4u;
+            const char* src0 = static_cast<const char*>(ix.vectors) + c.lane * lane_bytes;
+            const uint32_t dst0 = smem_u32(c.stg) + c.lane * lane_bytes;
+            const unsigned char* mine = c.stg + c.lane * lane_bytes;
             const int rb = (int)c.stg_rows;
+            const bool has_tail = ix.tail != 0;
             for (int j0 = 0; j0 < k; j0 += rb) {
                 const int nb = (k - j0) < rb ? (k - j0) : rb;
-                const uint32_t id = __shfl_sync(kFullMask, my_id, (j0 + c.lane) & 31);  // lane t: candidate j0 + t
-                __syncwarp();  // everyone is done reading the previous batch
-                if (c.lane == 0) mbar_arrive_expect_tx(c.bar, (uint32_t)nb * copy_bytes);
-                if (c.lane < nb)
-                    bulk_copy_g2s(smem_u32(c.stg) + c.lane * copy_bytes,
-                                  static_cast<const char*>(ix.vectors) + (size_t)id * stride_bytes, copy_bytes, c.bar,
-                                  c.pol_stream);
-                mbar_wait(c.bar, c.phase);
-                c.phase ^= 1u;
-                const unsigned char* mine = c.stg + c.lane * (V * 4);
-                for (int b = 0; b < nb; b += 4) {  // rows past nb hold stale data: computed, never used
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) c.tile[(b + u) * kTileStride + c.lane] = partial(mine + (b + u) * copy_bytes);
+                for (int b = 0; b < 8; ++b) {
+                    if (b >= nb) break;
+                    const uint32_t idb = __shfl_sync(kFullMask, my_id, j0 + b);
+                    const char* src = src0 + (size_t)idb * stride_bytes;
+#pragma unroll
+                    for (int g = 0; g < G; ++g)
+                        cp_async_lane<(int)lane_bytes>(dst0 + b * row_bytes + g * 32 * lane_bytes,
+                                                       src + g * 32 * lane_bytes);
+                }
+                cp_async_wait_all();
+#pragma unroll
+                for (int b = 0; b < 8; ++b) {
+                    if (b >= nb) break;
+                    c.tile[b * kTileStride + c.lane] = partial(mine + b * row_bytes);
                 }
                 __syncwarp();
+                uint32_t id = 0;
+                if (has_tail) id = __shfl_sync(kFullMask, my_id, (j0 + c.lane) & 31);  // lane t: candidate j0 + t
                 float db = 0.0f;
                 if (c.lane < nb) db = ordered_finish(ix, c, id, c.lane);
                 // hand the distance of candidate j0 + t (computed by lane t) to lane j0 + t
                 const float dj = __shfl_sync(kFullMask, db, (c.lane - j0) & 31);
                 if (c.lane >= j0 && c.lane < j0 + nb) d = dj;
+                __syncwarp();  // the next batch rewrites the tile
             }
-        } else if (c.lane < k) {
-            d = ordered_finish(ix, c, my_id, 0);
+        } else {
+            if (c.lane < k) d = ordered_finish(ix, c, my_id, 0);
+            __syncwarp();
         }
-        __syncwarp();
         return d;
     }
 };
@@ -355,6 +385,7 @@ struct DistF32 {
 // ANGULAR f32, any dim (runtime chunk count; natural row layout; query read from shared memory).
 struct DistF32Generic {
     static constexpr bool kStaged = false;
+    static constexpr bool kMbar = false;
     __device__ __forceinline__ void load_query(const DeviceIndex&, const WarpCtx&) {}
     __device__ __forceinline__ float dists(const DeviceIndex& ix, WarpCtx& c, uint32_t my_id, int k) {
         const float* base = static_cast<const float*>(ix.vectors);
@@ -390,6 +421,7 @@ struct DistF32Generic {
 // and the exact integer sums are reduced with REDUX (__reduce_add_sync) — integer addition is order independent.
 struct DistI8 {
     static constexpr bool kStaged = true;
+    static constexpr bool kMbar = true;
     __device__ __forceinline__ void load_query(const DeviceIndex&, const WarpCtx&) {}
     __device__ __forceinline__ float dists(const DeviceIndex& ix, WarpCtx& c, uint32_t my_id, int k) {
         const uint32_t stride = ix.row_stride;
@@ -440,6 +472,7 @@ struct DistI8 {
 // (src/elements/embeddings/mod.rs:124-143,164-174; src/math.rs:92-150).  Natural row layout, runtime dim.
 struct DistSum {
     static constexpr bool kStaged = false;
+    static constexpr bool kMbar = false;
     __device__ __forceinline__ void load_query(const DeviceIndex&, const WarpCtx&) {}
 
     // materialises ElementContainer::get(id) into c.xs (all lanes participate)
@@ -584,11 +617,13 @@ __device__ __forceinline__ bool vis_insert(uint32_t* tab, uint32_t slots, uint32
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Bucketed visited set for the fast pass (global memory, private to one warp): buckets of 8 u32 slots = one 32-byte
-// sector, filled from slot 0 upwards, 0xFFFFFFFF = empty.  A lookup is ONE sector read per lane (two 128-bit loads
-// that bypass L1); ids that are not found are inserted with plain stores — no atomics are needed because the table
-// has a single writer warp and conflicts between lanes of that warp are resolved in registers with match.any.
-// Returns true in lanes whose id was newly inserted.  Sets *overflow when a home bucket is full (-> slow path).
+// Bucketed visited set for the fast pass (global memory, private to one warp, L2 resident): buckets of 4 u32 slots
+// (16 bytes, one 128-bit load), filled from slot 0 upwards, 0xFFFFFFFF = empty; a full home bucket chains to the next
+// one.  A lookup is ONE load per lane; ids that are not found are inserted with plain stores — no atomics are needed
+// because the table has a single writer warp and conflicts between lanes of that warp are resolved in registers with
+// match.any.  Returns true in lanes whose id was newly inserted.  Sets *overflow when the chain gets too long
+// (-> retry pass with a larger table).  Every lane loads (lanes without a valid id read the bucket 0xFFFFFFFF hashes
+// to and ignore it), which keeps the probe free of predicate bookkeeping.
 // ------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint4 ldcg_u4(const uint32_t* p, unsigned long long policy) {
     uint4 v;
@@ -605,25 +640,18 @@ __device__ __forceinline__ void stcg_u4(uint4* p, uint4 v, unsigned long long po
                  "r"(v.w), "l"(policy)
                  : "memory");
 }
+constexpr uint32_t kVisHashMul = 0x9E3779B1u;
 __device__ __forceinline__ bool vis_bucket_insert(uint32_t* tab, uint32_t nbuckets, uint32_t id, bool valid,
                                                   bool* overflow, unsigned long long policy) {
-    uint32_t b = __umulhi(id * 0x9E3779B1u, nbuckets);
+    uint32_t b = __umulhi(id * kVisHashMul, nbuckets);
     bool pending = valid, is_new = false;
     for (int probe = 0;; ++probe) {
-        uint32_t* bucket = tab + (size_t)b * 8u;
-        uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
-        if (pending) {
-            lo = ldcg_u4(bucket, policy);
-            hi = ldcg_u4(bucket + 4, policy);
-        }
-        const bool found = (lo.x == id) | (lo.y == id) | (lo.z == id) | (lo.w == id) | (hi.x == id) |
-                           (hi.y == id) | (hi.z == id) | (hi.w == id);
-        // slots are filled in order, so the number of used slots is the index of the first empty one
-        const uint32_t used = (lo.x != kUnusedId) + (lo.y != kUnusedId) + (lo.z != kUnusedId) +
-                              (lo.w != kUnusedId) + (hi.x != kUnusedId) + (hi.y != kUnusedId) +
-                              (hi.z != kUnusedId) + (hi.w != kUnusedId);
-        if (pending && found) pending = false;
-        bool ins = pending && used < 8u;
+        uint32_t* bucket = tab + (size_t)b * 4u;
+        const uint4 v = ldcg_u4(bucket, policy);
+        const bool found = (v.x == id) | (v.y == id) | (v.z == id) | (v.w == id);
+        pending = pending && !found;
+        // slots are filled in order: the bucket is full iff its last slot is used
+        bool ins = pending && (v.w == kUnusedId);
         const unsigned ins_mask = __ballot_sync(kFullMask, ins);
         if (ins_mask) {
             // the same id twice in one neighbour list (MultiSetVector allows duplicates): only the first lane inserts
@@ -635,8 +663,9 @@ __device__ __forceinline__ bool vis_bucket_insert(uint32_t* tab, uint32_t nbucke
             // new ids that share a bucket take consecutive free slots
             const unsigned same_b = __match_any_sync(kFullMask, b) & __ballot_sync(kFullMask, ins);
             if (ins) {
+                const uint32_t used = (v.x != kUnusedId) + (v.y != kUnusedId) + (v.z != kUnusedId);
                 const uint32_t slot = used + __popc(same_b & lanemask_lt());
-                if (slot < 8u) {
+                if (slot < 4u) {
                     stcg_u32(bucket + slot, id, policy);
                     is_new = true;
                     pending = false;
@@ -874,14 +903,18 @@ __device__ __forceinline__ void search_layer(const DeviceIndex& ix, WarpCtx& c, 
 
 // ------------------------------------------------------------------------------------------------------------------
 // search_for_neighbors, fast variant: same state machine as search_layer (above) with a cheaper list representation.
-//   * keys are split into two u32 arrays in shared memory: Ld[j] = distance bits | expanded flag (bit 31) and
-//     Li[j] = id, sorted by (distance, id); capacity is 32*R (R compile time, odd -> conflict-free lane-major access);
-//     Ld is padded to a power of two with sentinels so the rank search is a branch-free lower bound;
-//   * all passing keys of one expansion are merged in one pass: every lane finds the rank of its key, then each lane
-//     (owning positions [R*l, R*l+R)) counts how many new keys land at or before each of its entries and moves them
-//     through registers (read everything, sync, write), so the merge is race free in place;
+//   * keys are split into two u32 arrays in SHARED memory (`Ld` must point into the kernel's shared window so that
+//     every access is an LDS/STS with a 32-bit address): Ld[j] = distance bits | expanded flag (bit 31), Li[j] = id,
+//     sorted by (distance, id); capacity 32*R, position j lives in bank j % 32 (row-major: row r = positions
+//     [32r, 32r+32)); Ld is padded to a power of two with flagged +inf-like sentinels, so the rank search is a
+//     branch-free lower bound and the pop scan needs no length check;
+//   * all passing keys of one expansion are merged in one pass: every lane ranks its key among the old entries
+//     (lower bound) and among the other new keys (compare loop over the keys parked in shared memory), which gives the
+//     final position of every new key; the rows of the list at or after the first insertion point are then rebuilt
+//     top-down as a GATHER: output position p either receives a new key or the old entry p - (#new keys below p),
+//     where the count comes from a per-row occupancy mask (REDUX.OR) and popc — one LDS/STS pair per array and row;
 //   * keys strictly farther than the tail of a full list are dropped up front (they can never matter);
-//   * the visited set is the bucketed global-memory table (vis_bucket_insert): one sector read per neighbour.
+//   * the visited set is the bucketed global-memory table (vis_bucket_insert): one 16-byte load per neighbour.
 // ------------------------------------------------------------------------------------------------------------------
 __host__ __device__ constexpr uint32_t fast_list_pow2(int R) {
     uint32_t p = 32;
@@ -892,22 +925,24 @@ __host__ __device__ constexpr uint32_t fast_list_pow2(int R) {
 __host__ __device__ constexpr uint32_t fast_list_bytes(int R) { return (fast_list_pow2(R) + 32u * (uint32_t)R) * 4u; }
 
 template <class Dist, int R>
-__device__ __forceinline__ void search_layer_fast(const DeviceIndex& ix, WarpCtx& c, Dist& dist, const uint32_t* rows,
-                                                  const uint32_t width, const uint32_t entrypoint, const uint32_t ef,
+__device__ __forceinline__ void search_layer_fast(const DeviceIndex& ix, WarpCtx& c, Dist& dist, uint32_t* Ld,
+                                                  const uint32_t* rows, const uint32_t width,
+                                                  const uint32_t entrypoint, const uint32_t ef,
                                                   const uint32_t vis_slots, uint32_t* out_n) {
     constexpr uint32_t cap = 32u * R;
-    constexpr uint32_t P = fast_list_pow2(R);  // Ld is padded to a power of two > cap with +inf-like sentinels
+    constexpr uint32_t P = fast_list_pow2(R);  // Ld is padded to a power of two > cap with sentinels
     constexpr uint32_t kFlag = 0x80000000u, kDMask = 0x7FFFFFFFu;
-    uint32_t* Ld = reinterpret_cast<uint32_t*>(c.list);
     uint32_t* Li = Ld + P;
     const int lane = c.lane;
-    const uint32_t nbuckets = vis_slots >> 3;
+    const unsigned lt = lanemask_lt();
+    const uint32_t nbuckets = vis_slots >> 2;
     {
         uint4* v4 = reinterpret_cast<uint4*>(c.visited);
         const uint4 e = make_uint4(kUnusedId, kUnusedId, kUnusedId, kUnusedId);
-        for (uint32_t i = lane; i < nbuckets * 2; i += 32) stcg_u4(v4 + i, e, c.pol_keep);
+        for (uint32_t i = lane; i < nbuckets; i += 32) stcg_u4(v4 + i, e, c.pol_keep);
     }
-    for (uint32_t i = lane; i < P; i += 32) Ld[i] = kDMask;  // sentinel: larger than any distance, never flagged
+    // sentinel: masked distance larger than any real one; flagged, so the pop scan never selects it
+    for (uint32_t i = lane; i < P; i += 32) Ld[i] = 0xFFFFFFFFu;
     __syncwarp();
     const uint32_t vis_limit = vis_slots - (vis_slots >> 2);  // keep the bucket load factor <= 3/4
     uint32_t vis_count = 1;
@@ -938,8 +973,7 @@ __device__ __forceinline__ void search_layer_fast(const DeviceIndex& ix, WarpCtx
         unsigned sel_mask = 0;
         for (; base_sel < n; base_sel += 32) {
             const uint32_t j = base_sel + lane;
-            const bool un = (j < n) && (j >= cursor) && !(Ld[j] & kFlag);
-            sel_mask = __ballot_sync(kFullMask, un);
+            sel_mask = __ballot_sync(kFullMask, (j >= cursor) && !(Ld[j] & kFlag));  // positions >= n are flagged
             if (sel_mask) {
                 px = base_sel + __ffs(sel_mask) - 1;
                 break;
@@ -952,11 +986,8 @@ __device__ __forceinline__ void search_layer_fast(const DeviceIndex& ix, WarpCtx
         // Speculation: the runner-up of this pop (next unexpanded entry of the same 32-entry row) is the most likely
         // next expansion.  Its adjacency row is loaded into a register now (one lane = one neighbour, width <= 32)
         // so that the load latency overlaps this whole expansion; a wrong guess only costs the load.
-        uint32_t cur_nb = kUnusedId;
         const bool have_cur = (spec_id == xid) && (width <= 32u);
-        if (have_cur) {
-            cur_nb = spec_nb;
-        }
+        const uint32_t cur_nb = spec_nb;
         spec_id = kUnusedId;
         {
             const unsigned rest = sel_mask & (sel_mask - 1);
@@ -1017,7 +1048,7 @@ __device__ __forceinline__ void search_layer_fast(const DeviceIndex& ix, WarpCtx
                 return;
             }
             if (k == 0) continue;
-            if (is_new) c.ids[__popc(nm & lanemask_lt())] = nb;
+            if (is_new) c.ids[__popc(nm & lt)] = nb;
             __syncwarp();
             const uint32_t my_id = c.ids[lane < k ? lane : 0];
             c.n_dist += k;
@@ -1028,11 +1059,18 @@ __device__ __forceinline__ void search_layer_fast(const DeviceIndex& ix, WarpCtx
                 return;
             }
             const uint32_t my_d = __float_as_uint(d);
-            if (spec_id != kUnusedId && spec_nb != kUnusedId) {
-                // the speculative row has had a whole distance phase to arrive: warm L2 with its visited buckets
-                const uint32_t pb = __umulhi(spec_nb * 0x9E3779B1u, nbuckets);
-                asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(c.visited + (size_t)pb * 8u));
-            }
+            // The speculative row has had a whole distance phase to arrive: warm L2 with its visited buckets.  The
+            // whole address computation sits in one volatile asm so that no use of spec_nb can be hoisted to where
+            // the load was issued (that would expose the load's latency in every expansion).
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t.reg .b32 h, t;\n\t.reg .b64 a;\n\t"
+                "setp.ne.u32 p, %0, 0xffffffff;\n\t"
+                "mul.lo.u32 h, %0, 0x9E3779B1;\n\t"
+                "mul.hi.u32 t, h, %1;\n\t"
+                "mad.wide.u32 a, t, 16, %2;\n\t"
+                "@p prefetch.global.L2::evict_last [a];\n\t}" ::"r"(spec_nb),
+                "r"(nbuckets), "l"(c.visited)
+                : "memory");
             // !res.is_full() || distance < res.peek().0   (:1029)
             bool pass = (lane < k) && (n_exp < ef || my_d < thr_bits);
             // a key strictly farther than the last entry of a full list has >= ef strictly closer entries before
@@ -1042,6 +1080,9 @@ __device__ __forceinline__ void search_layer_fast(const DeviceIndex& ix, WarpCtx
             if (pm == 0) continue;
             const uint32_t m = __popc(pm);
 
+            // park the passing keys (compacted) in shared memory: key t = (id, distance bits) as one 64-bit word
+            uint2* keys = reinterpret_cast<uint2*>(c.ids + 32);
+            if (pass) keys[__popc(pm & lt)] = make_uint2(my_id, my_d);
             // rank of my key among the entries: branch-free lower bound on the distance over the padded array
             // (entries at positions >= n are sentinels), refined by id on exact distance ties
             uint32_t lo = 0;
@@ -1049,50 +1090,48 @@ __device__ __forceinline__ void search_layer_fast(const DeviceIndex& ix, WarpCtx
             for (uint32_t step = P / 2; step >= 1; step >>= 1)
                 if ((Ld[lo + step - 1] & kDMask) < my_d) lo += step;
             while (lo < n && (Ld[lo] & kDMask) == my_d && Li[lo] < my_id) ++lo;  // (d, id) tuple order
-            const uint32_t rank_l = lo;
-            // my entries (lane-major: lane l owns positions [R*l, R*l+R)) and how far each one moves:
-            // sh(j) = number of new keys ranked at or before entry j;  my key lands at rank_l + #smaller new keys
-            uint32_t dv[R], iv[R], sh[R];
-#pragma unroll
-            for (int t = 0; t < R; ++t) {
-                const uint32_t j = R * lane + t;
-                dv[t] = Ld[j];  // positions >= n hold sentinels (Ld is padded), Li is only read below n
-                iv[t] = j < n ? Li[j] : 0u;
-                sh[t] = 0;
+            __syncwarp();
+            // rank among the new keys (ids are distinct, so the 64-bit (distance, id) keys are too)
+            uint32_t rank_n = 0;
+            for (uint32_t t = 0; t < m; ++t) {
+                const uint2 kt = keys[t];
+                rank_n += (kt.y < my_d || (kt.y == my_d && kt.x < my_id)) ? 1u : 0u;
             }
-            uint32_t rank_n = 0, sh_base = 0;
-            for (unsigned t = pm; t; t &= t - 1) {
-                const int j = __ffs(t) - 1;
-                const uint32_t rj = __shfl_sync(kFullMask, rank_l, j);
-                const uint32_t dj = __shfl_sync(kFullMask, my_d, j);
-                const uint32_t ij = __shfl_sync(kFullMask, my_id, j);
-                rank_n += (dj < my_d || (dj == my_d && ij < my_id)) ? 1u : 0u;
-                // keys ranked before my first position shift all my entries; a key ranked inside my R positions
-                // (rare) shifts only the entries at or after it
-                const uint32_t rel = rj - (uint32_t)(R * lane);  // wraps to a huge value when rj < R*lane
-                if (rj <= (uint32_t)(R * lane)) {
-                    sh_base += 1;
-                } else if (rel < (uint32_t)R) {
-#pragma unroll
-                    for (int tt = 0; tt < R; ++tt) sh[tt] += (rel <= (uint32_t)tt) ? 1u : 0u;
-                }
-            }
-#pragma unroll
-            for (int tt = 0; tt < R; ++tt) sh[tt] += sh_base;
-            const uint32_t new_pos = rank_l + rank_n;
+            const uint32_t new_pos = lo + rank_n;
             const uint32_t total = n + m;
-            uint32_t drop_flagged = 0;
-            __syncwarp();  // every lane holds its entries in registers: the list can be rewritten in place
+            const uint32_t min_pos = warp_min_u32(kFullMask, pass ? new_pos : 0xFFFFFFFFu);
+            uint32_t drop_flagged = 0, mdrop = 0;
+            if (total > cap) {
+                // the last (total - cap) positions of the merged order fall off: mdrop new keys and odrop old entries
+                mdrop = __popc(__ballot_sync(kFullMask, pass && new_pos >= cap));
+                const uint32_t odrop = (total - cap) - mdrop;
+                const uint32_t j = n - odrop + lane;
+                drop_flagged = __popc(__ballot_sync(kFullMask, ((uint32_t)lane < odrop) && (Ld[j] >> 31)));
+            }
+            const uint32_t kept = total > cap ? cap : total;
+            // rebuild rows top-down: output position p takes the old entry p - (#new keys below p) unless a new key
+            // lands there.  A row only reads old positions <= its own, so writing it after a barrier is race free.
+            {
+                uint32_t kge = mdrop;  // new keys at positions >= the end of the current row
+                const int rt = (int)((kept - 1) >> 5), rbm = (int)(min_pos >> 5);
 #pragma unroll
-            for (int t = 0; t < R; ++t) {
-                const uint32_t j = R * lane + t;
-                if (j < n && sh[t] > 0) {
-                    const uint32_t np = j + sh[t];
-                    if (np < cap) {
-                        Ld[np] = dv[t];
-                        Li[np] = iv[t];
-                    } else {
-                        drop_flagged += dv[t] >> 31;
+                for (int r = R - 1; r >= 0; --r) {
+                    if (r > rt || r < rbm) continue;
+                    const unsigned occ = __reduce_or_sync(
+                        kFullMask, (pass && (new_pos >> 5) == (uint32_t)r) ? (1u << (new_pos & 31)) : 0u);
+                    kge += __popc(occ);
+                    const uint32_t p = 32u * r + lane;
+                    const uint32_t below = (m - kge) + __popc(occ & lt);  // new keys at positions < p
+                    const bool old = !((occ >> lane) & 1u) && p < kept && p >= min_pos;
+                    uint32_t vd = 0, vi = 0;
+                    if (old) {
+                        vd = Ld[p - below];
+                        vi = Li[p - below];
+                    }
+                    __syncwarp();
+                    if (old) {
+                        Ld[p] = vd;
+                        Li[p] = vi;
                     }
                 }
             }
@@ -1104,7 +1143,7 @@ __device__ __forceinline__ void search_layer_fast(const DeviceIndex& ix, WarpCtx
             if (total > cap) {
                 n = cap;
                 // entries fell off the end: legal only if >= ef strictly closer entries remain; everything dropped is
-                // >= the last kept entry, so "L[ef-1].d < L[cap-1].d" is sufficient (else: slow path)
+                // >= the last kept entry, so "L[ef-1].d < L[cap-1].d" is sufficient (else: retry / slow path)
                 if (!((Ld[ef - 1] & kDMask) < (Ld[cap - 1] & kDMask))) {
                     c.status |= kStatusOverflow;
                     *out_n = n;
@@ -1123,13 +1162,12 @@ __device__ __forceinline__ void search_layer_fast(const DeviceIndex& ix, WarpCtx
                         pos_thr += m;
                     }
                 } else {
-                    n_exp -= __reduce_add_sync(kFullMask, drop_flagged);
+                    n_exp -= drop_flagged;
                 }
             } else {
                 n = total;
                 if (n_exp >= ef) pos_thr += m;
             }
-            const uint32_t min_pos = warp_min_u32(kFullMask, pass ? new_pos : 0xFFFFFFFFu);
             if (min_pos < cursor) cursor = min_pos;
         }
     }
@@ -1318,10 +1356,13 @@ __global__ void __launch_bounds__(32, R > 0 ? GB_MIN_BLOCKS : 1) search_kernel(c
         c.stg = sp;
         sp += (size_t)a.stg_rows * a.stg_row_bytes;
     }
-    if (Dist::kStaged) {
+    if (Dist::kMbar) {
         if (c.lane == 0) mbar_init(c.bar, 1);
         __syncwarp();
     }
+    // the fast list always lives in this CTA's shared window (derived from smem_raw only, so that the compiler keeps
+    // its accesses in the shared address space: LDS/STS with 32-bit addresses)
+    uint32_t* const fast_list = reinterpret_cast<uint32_t*>(sp);
     uint32_t list_cap, vis_slots, vis_upper;
     if (a.slow_pass) {
         c.list = a.slow_list + (size_t)blockIdx.x * a.slow_list_cap;
@@ -1405,10 +1446,10 @@ __global__ void __launch_bounds__(32, R > 0 ? GB_MIN_BLOCKS : 1) search_kernel(c
                 }
             } else {
                 constexpr int RB = R > 0 ? R : 1;
-                const uint32_t* Ld = reinterpret_cast<const uint32_t*>(c.list);
+                const uint32_t* Ld = fast_list;
                 for (int l = 0; l < bl && c.status == 0; ++l) {
-                    search_layer_fast<Dist, 1>(ix, c, dist, ix.layer_rows[l], ix.layer_width[l], entrypoint, 1u,
-                                               vis_upper, &n);
+                    search_layer_fast<Dist, 1>(ix, c, dist, fast_list, ix.layer_rows[l], ix.layer_width[l],
+                                               entrypoint, 1u, vis_upper, &n);
                     if (c.status) break;
                     uint32_t ep = 0;  // res[0] (capacity 32: a single row)
                     const unsigned m = __ballot_sync(kFullMask, ((uint32_t)c.lane < n) && (Ld[c.lane] >> 31));
@@ -1416,8 +1457,8 @@ __global__ void __launch_bounds__(32, R > 0 ? GB_MIN_BLOCKS : 1) search_kernel(c
                     entrypoint = ep;
                 }
                 if (c.status == 0)
-                    search_layer_fast<Dist, RB>(ix, c, dist, ix.layer_rows[bl], ix.layer_width[bl], entrypoint,
-                                                a.max_search, vis_slots, &n);
+                    search_layer_fast<Dist, RB>(ix, c, dist, fast_list, ix.layer_rows[bl], ix.layer_width[bl],
+                                                entrypoint, a.max_search, vis_slots, &n);
                 if (c.status == 0) {
                     const uint32_t* Li = Ld + fast_list_pow2(RB);
                     const uint32_t limit = a.max_search < k ? a.max_search : k;
