@@ -51,7 +51,8 @@ constexpr unsigned long long kFlagExpanded = 1ull << 63;
 constexpr unsigned long long kKeyMask = ~kFlagExpanded;
 constexpr unsigned kFullMask = 0xFFFFFFFFu;
 constexpr int kTileStride = 36;  // floats per tile row: 16-byte aligned rows, conflict-free LDS.128 per quarter warp
-constexpr int kIdScratchBytes = 384;  // 32 x u32 compacted candidate ids + 32 x (id, distance bits) keys of a merge
+// 32 x u32 compacted candidate ids | 32 x (id, distance bits) keys of a merge | 2 x 32 u32 speculative adjacency rows
+constexpr int kIdScratchBytes = 640;
 __host__ __device__ constexpr uint32_t tile_bytes_for_rows(uint32_t rows) { return rows * kTileStride * 4u + kIdScratchBytes; }
 
 enum ElementKind : int { kAngularF32 = 0, kAngularI8 = 1, kSumEmbeddings = 2 };
@@ -251,6 +252,9 @@ __device__ __forceinline__ void cp_async_lane(uint32_t dst, const void* src) {
         asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// waits until at most the most recently committed group is still in flight
+__device__ __forceinline__ void cp_async_wait_but_last() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
 // Strictly ordered sum of the 32 lane partials of ONE value (used where only a single candidate is live):
 // r = 0; for i in 0..32 { r += chunk[i] }   (src/math.rs:27-30).  All lanes return the same r.
@@ -964,7 +968,8 @@ __device__ __forceinline__ void search_layer_fast(const DeviceIndex& ix, WarpCtx
         __syncwarp();
     }
     uint32_t n = 1, n_exp = 0, cursor = 0, pos_thr = 0, thr_bits = 0;
-    uint32_t spec_id = kUnusedId, spec_nb = kUnusedId;
+    uint32_t spec_id = kUnusedId, spec_slot = 0;
+    uint32_t* const spec_rows = c.ids + 96;
 
     while (true) {
         // ---- pq.pop(): first unexpanded entry at or after the cursor; also find the runner-up ----
@@ -984,17 +989,23 @@ __device__ __forceinline__ void search_layer_fast(const DeviceIndex& ix, WarpCtx
         const uint32_t xid = Li[px];
         if (n_exp >= ef && xd > thr_bits) break;
         // Speculation: the runner-up of this pop (next unexpanded entry of the same 32-entry row) is the most likely
-        // next expansion.  Its adjacency row is loaded into a register now (one lane = one neighbour, width <= 32)
-        // so that the load latency overlaps this whole expansion; a wrong guess only costs the load.
+        // next expansion.  Its adjacency row (one lane = one neighbour, width <= 32) is fetched NOW with cp.async
+        // into one of two shared slots so that the load latency overlaps this whole expansion; a wrong guess only
+        // costs the load.  (A register destination would not work: the consumer of the previous speculation would
+        // wait on the same scoreboard as the load issued here.)  Every pop commits exactly one — possibly empty —
+        // group, so "all groups but the last" at the consumer is precisely the previous pop's row.
         const bool have_cur = (spec_id == xid) && (width <= 32u);
-        const uint32_t cur_nb = spec_nb;
+        const uint32_t* cur_row = spec_rows + 32u * spec_slot;
         spec_id = kUnusedId;
         {
             const unsigned rest = sel_mask & (sel_mask - 1);
             if (rest && width <= 32u) {
+                spec_slot ^= 1u;
                 spec_id = Li[base_sel + __ffs(rest) - 1];
-                spec_nb = ((uint32_t)lane < width) ? __ldg(rows + (size_t)spec_id * width + lane) : kUnusedId;
+                if ((uint32_t)lane < width)
+                    cp_async_lane<4>(smem_u32(spec_rows + 32u * spec_slot + lane), rows + (size_t)spec_id * width + lane);
             }
+            cp_async_commit();
         }
 
         // ---- res.push ----
@@ -1032,7 +1043,13 @@ __device__ __forceinline__ void search_layer_fast(const DeviceIndex& ix, WarpCtx
         // ---- neighbours ----
         const uint32_t* row = rows + (size_t)xid * width;
         for (uint32_t w0 = 0; w0 < width; w0 += 32) {
-            const uint32_t nb = have_cur ? cur_nb : ((w0 + lane < width) ? __ldg(row + w0 + lane) : kUnusedId);
+            uint32_t nb = kUnusedId;
+            if (have_cur) {
+                cp_async_wait_but_last();
+                if ((uint32_t)lane < width) nb = cur_row[lane];
+            } else if (w0 + lane < width) {
+                nb = __ldg(row + w0 + lane);
+            }
             const bool valid = nb != kUnusedId;
             const unsigned vm = __ballot_sync(kFullMask, valid);
             if (vm == 0) break;
@@ -1059,18 +1076,14 @@ __device__ __forceinline__ void search_layer_fast(const DeviceIndex& ix, WarpCtx
                 return;
             }
             const uint32_t my_d = __float_as_uint(d);
-            // The speculative row has had a whole distance phase to arrive: warm L2 with its visited buckets.  The
-            // whole address computation sits in one volatile asm so that no use of spec_nb can be hoisted to where
-            // the load was issued (that would expose the load's latency in every expansion).
-            asm volatile(
-                "{\n\t.reg .pred p;\n\t.reg .b32 h, t;\n\t.reg .b64 a;\n\t"
-                "setp.ne.u32 p, %0, 0xffffffff;\n\t"
-                "mul.lo.u32 h, %0, 0x9E3779B1;\n\t"
-                "mul.hi.u32 t, h, %1;\n\t"
-                "mad.wide.u32 a, t, 16, %2;\n\t"
-                "@p prefetch.global.L2::evict_last [a];\n\t}" ::"r"(spec_nb),
-                "r"(nbuckets), "l"(c.visited)
-                : "memory");
+            // The speculative row arrived with this expansion's candidate rows (same cp.async wait): warm L2 with
+            // the visited buckets of its neighbours.
+            if (spec_id != kUnusedId && (uint32_t)lane < width) {
+                const uint32_t sn = spec_rows[32u * spec_slot + lane];
+                if (sn != kUnusedId)
+                    asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(
+                        c.visited + (size_t)__umulhi(sn * kVisHashMul, nbuckets) * 4u));
+            }
             // !res.is_full() || distance < res.peek().0   (:1029)
             bool pass = (lane < k) && (n_exp < ef || my_d < thr_bits);
             // a key strictly farther than the last entry of a full list has >= ef strictly closer entries before
