@@ -1,24 +1,34 @@
 #!/usr/bin/env python
 """bench.py — QPS of the granne search path on B200 (BASELINE.json metric), with roofline, e2e and CPU baseline.
 
-Workload (config.workload): BASELINE.json configs[1] — 1M x 128-d angular f32, M=30, build max_search=200, search
-max_search=200, k=10, batches of 1024 queries per GPU per step — the largest configuration of the metric's family that
-this bench can BUILD inside its time budget (the 100M x 128 configuration of the headline fits one GPU's HBM, but no
-100M-element HNSW index can be constructed in minutes).  Synthetic clustered vectors
- so that recall@10 >= 0.95 is reachable; recall is measured against an exact brute force and reported.
+Workload (config.workload).  The default is BASELINE.json configs[3], the configuration the metric is quoted on:
+100M x 128-d angular f32, M=30, build max_search=200, search max_search=200, k=10, index replicated on every GPU,
+1024 queries per GPU per step (it fits one GPU: 51 GB of vectors + 13 GB of adjacency rows).  `--config c2|c3|c5`
+select the other BASELINE configurations (1M x 128 f32; 10M x 100 i8; range-partitioned i8 shards, one per GPU),
+`--elements` overrides the element count.  Synthetic clustered vectors so that recall@10 >= 0.95 is
+reachable; recall is measured against an exact brute force and reported.
+
+Setup (outside the timed region): the vectors are generated ON THE GPU (seeded torch generators, element-wise
+arithmetic only, so every rank and both arms produce the same bits), turned into elements by the library
+(Vector::from per row) and handed over as a device-resident container; the index is built once per box by the GPU
+GranneBuilder and its granne FILE IMAGE is cached under /dev/shm, so that every later run on the box — other N, and
+the reference arm — loads the very same index bytes.
 
 One step = one batch of 1024 queries per rank through Granne::search semantics (granne_b200_search_batch*).  Steps
 are independent batches; they are issued round-robin on 8 CUDA streams (a serving system would do the same), then
 the whole timed region is bracketed by barrier + synchronize and timed with CUDA events (max over ranks).
-  value   device-resident: queries already in HBM, results left in HBM (+ NCCL all-gather of the result tiles, N > 1)
-  e2e     host buffers through the public API (granne_b200.Granne.search_batch): H2D of the queries and D2H of the
-          results inside the timed region, issued from a few host threads
-Multi-GPU: the index is replicated (rank 0 builds, the file image is broadcast), every rank searches its own 1024
-queries per step ("weak" scaling: per-GPU work fixed), results are all-gathered.
+  value   device-resident: queries already in HBM, results left in HBM (+ the fused peer-store gather, N > 1)
+  e2e     host buffers through the public API (granne_b200.Granne.search_batch -> granne_b200_search_batch): H2D of
+          the queries and D2H of the results inside the timed region, issued from persistent host threads
+Multi-GPU: replicated mode = every rank searches its own 1024 queries per step ("weak" scaling: per-GPU work fixed),
+results gathered by peer stores; partitioned mode (`--config c5` / `--mode partitioned`) = one independent index per
+rank, every rank searches ALL queries of the step on its shard, the tiles are all-gathered and merged by
+(distance, global id) on the GPU inside the timed region.
 
-`--impl reference` times the CPU restatement of the reference (oracle/, all host threads) on the same configuration.
+`--impl reference` times the CPU restatement of the reference (oracle/, all host threads) on the same index image.
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -32,8 +42,20 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-METRIC = "QPS @ recall@10>=0.95, angular f32 HNSW search (granne Granne::search), per-box aggregate"
+METRIC = "QPS @ recall@10>=0.95, angular HNSW search (granne Granne::search), per-box aggregate"
 UNIT = "queries/s"
+GEN_VERSION = 2          # bump when the synthetic generator changes (part of the cache key)
+CHUNK = 1 << 20          # rows per generation chunk (the generator is seeded per chunk)
+DATA_SEED, QUERY_SEED = 1234, 4321
+
+CONFIGS = {
+    # name: (kind, n, dim, mode, BASELINE.json config it stands for)
+    "c2": ("angular", 1_000_000, 128, "replicated", "BASELINE.json configs[1]"),
+    "c3": ("angular_int", 10_000_000, 100, "replicated", "BASELINE.json configs[2]"),
+    "c4": ("angular", 100_000_000, 128, "replicated", "BASELINE.json configs[3]"),
+    "c5": ("angular_int", 12_500_000, 96, "partitioned", "BASELINE.json configs[4] family (1B/8 = 125M per shard "
+                                                          "scaled to what builds in the time budget)"),
+}
 
 
 def parse_args():
@@ -42,28 +64,51 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--elements", dest="n", type=int, default=1_000_000,
-                    help="number of indexed elements (not --n: torchrun would claim that prefix)")
-    ap.add_argument("--dim", type=int, default=128)
-    ap.add_argument("--nq", type=int, default=1024, help="queries per step per GPU")
+    ap.add_argument("--config", default=os.environ.get("GRANNE_B200_BENCH_CONFIG", "c4"), choices=sorted(CONFIGS))
+    ap.add_argument("--elements", dest="n", type=int, default=0,
+                    help="number of indexed elements (per shard in partitioned mode); 0 = the config's own "
+                         "(not --n: torchrun would claim that prefix)")
+    ap.add_argument("--dim", type=int, default=0)
+    ap.add_argument("--kind", default="", choices=["", "angular", "angular_int"])
+    ap.add_argument("--mode", default="", choices=["", "replicated", "partitioned"])
+    ap.add_argument("--nq", type=int, default=1024, help="queries per step (per GPU in replicated mode)")
     ap.add_argument("--max-search", type=int, default=200)
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--num-neighbors", type=int, default=30)
     ap.add_argument("--streams", type=int, default=8)
-    ap.add_argument("--graphs", type=int, default=0, help="replay each step from a CUDA graph (0 = eager launches)")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
-                    help="N > 1: p2p = kernels store result tiles into every peer's buffer (fused epilogue over "
-                         "NVLink peer memory); nccl = one all-gather per step")
-    ap.add_argument("--kind", default="angular", choices=["angular", "angular_int"],
-                    help="element type (angular_int = BASELINE config 3 style i8/dp4a path)")
-    ap.add_argument("--reorder", type=int, default=0,
-                    help="1: run Granne::reorder (GPU compute_order + host apply) on the built index before searching")
+                    help="replicated, N > 1: p2p = kernels store result tiles into every peer's buffer (fused "
+                         "epilogue over NVLink peer memory); nccl = one all-gather per step")
+    ap.add_argument("--dist", default="clustered", choices=["clustered", "uniform"],
+                    help="uniform = the reference's own test distribution U(-0.5, 0.5) (src/test_helper.rs:3-6)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target duration of the cpu_baseline sample")
-    return ap.parse_args()
+    ap.add_argument("--cache", default=os.environ.get("GRANNE_B200_BENCH_CACHE", "/dev/shm/granne_b200_bench_cache"),
+                    help="directory for the index file image shared by all runs on this box ('' = no cache)")
+    ap.add_argument("--no-fallback", action="store_true", help="fail instead of retrying with 10x fewer elements")
+    a = ap.parse_args()
+    kind, n, dim, mode, base = CONFIGS[a.config]
+    a.kind = a.kind or kind
+    a.n = a.n or n
+    a.dim = a.dim or dim
+    a.mode = a.mode or mode
+    a.baseline_config = base
+    return a
+
+
+# ---- synthetic data ----------------------------------------------------------------------------------------------------
+def mixture(n, dim, sub_dim=16, basis_seed=7):
+    """Gaussian mixture on a random low-dimensional subspace (SURVEY.md §8d measurement distribution): the small
+    basis / centre tables are made on the host, the points on the device."""
+    n_centers = max(8, int(4096 * (n / 1e6) ** 0.5))
+    brng = np.random.default_rng(basis_seed)
+    basis = brng.standard_normal((sub_dim, dim)).astype(np.float32)
+    centers = brng.standard_normal((n_centers, sub_dim)).astype(np.float32)
+    return basis, centers
 
 
 def clustered(n, dim, seed, n_centers, sub_dim=16, spread=0.3, basis_seed=7):
-    """Gaussian mixture on a random low-dimensional subspace (SURVEY.md §8d measurement distribution)."""
+    """Host (numpy) version of the same mixture, for tests and tools that need host arrays (tests/test_fullsize_gpu.py,
+    tools/prof_search.py); bench.py itself generates on the device."""
     brng = np.random.default_rng(basis_seed)
     basis = brng.standard_normal((sub_dim, dim)).astype(np.float32)
     centers = brng.standard_normal((n_centers, sub_dim)).astype(np.float32)
@@ -78,23 +123,132 @@ def clustered(n, dim, seed, n_centers, sub_dim=16, spread=0.3, basis_seed=7):
     return out
 
 
-def workload_config(a, impl):
+def raw_chunk_device(torch, dev, a, tables, seed, chunk_index, rows, spread=0.3):
+    """`rows` raw vectors of chunk `chunk_index` of stream `seed` as a CUDA float32 tensor.  Seeded per chunk, only
+    element-wise arithmetic (no GEMM), so the same (seed, chunk) gives the same bits in every process on this GPU type."""
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed * 1000003 + chunk_index)
+    if a.dist == "uniform":
+        return torch.rand((rows, a.dim), generator=g, device=dev, dtype=torch.float32) - 0.5
+    basis, centers = tables
+    which = torch.randint(0, centers.shape[0], (rows,), generator=g, device=dev)
+    pts = centers[which] + spread * torch.randn((rows, centers.shape[1]), generator=g, device=dev, dtype=torch.float32)
+    out = torch.zeros((rows, a.dim), device=dev, dtype=torch.float32)
+    for k in range(basis.shape[0]):
+        out.addcmul_(pts[:, k:k + 1], basis[k:k + 1])
+    return out
+
+
+def device_tables(torch, dev, a, n_total):
+    if a.dist == "uniform":
+        return None
+    basis, centers = mixture(n_total, a.dim)
+    return torch.from_numpy(basis).to(dev), torch.from_numpy(centers).to(dev)
+
+
+def make_elements_device(torch, granne_b200, dev, a, n, seed, tables):
+    """The element container [n, dim] (normalised f32 / i8) in HBM, generated chunk by chunk."""
+    dt = torch.int8 if a.kind == "angular_int" else torch.float32
+    el = torch.empty((n, a.dim), dtype=dt, device=dev)
+    for ci, s in enumerate(range(0, n, CHUNK)):
+        m = min(CHUNK, n - s)
+        raw = raw_chunk_device(torch, dev, a, tables, seed, ci, m)
+        granne_b200.elements_from_raw_device(a.kind, raw, out=el[s:s + m])
+        del raw
+    torch.cuda.synchronize(dev)
+    return el
+
+
+def make_queries_device(torch, dev, a, nq_total, seed, tables):
+    out = torch.empty((nq_total, a.dim), dtype=torch.float32, device=dev)
+    for ci, s in enumerate(range(0, nq_total, CHUNK)):
+        m = min(CHUNK, nq_total - s)
+        out[s:s + m] = raw_chunk_device(torch, dev, a, tables, seed, ci, m)
+    return out
+
+
+# ---- index cache -------------------------------------------------------------------------------------------------------
+def cache_path(a, n, seed):
+    if not a.cache:
+        return None
+    key = "%s_%dx%d_M%d_ef200_%s_seed%d_gen%d" % (a.kind, n, a.dim, a.num_neighbors, a.dist, seed, GEN_VERSION)
+    return os.path.join(a.cache, key + ".granne")
+
+
+def cache_load(path):
+    if path and os.path.exists(path) and os.path.exists(path + ".json"):
+        try:
+            meta = json.load(open(path + ".json"))
+            data = np.fromfile(path, dtype=np.uint8)
+            if data.size == meta["bytes"] and hashlib.sha1(data[:1 << 20].tobytes()).hexdigest() == meta["head_sha1"]:
+                return data, meta
+        except Exception:
+            pass
+    return None, None
+
+
+def cache_store(path, index_bytes, meta):
+    if not path:
+        return
+    try:
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        tmp = "%s.tmp.%d" % (path, os.getpid())
+        np.asarray(index_bytes).tofile(tmp)
+        meta = dict(meta, bytes=int(np.asarray(index_bytes).size),
+                    head_sha1=hashlib.sha1(np.asarray(index_bytes)[:1 << 20].tobytes()).hexdigest())
+        json.dump(meta, open(tmp + ".json", "w"))
+        os.replace(tmp + ".json", path + ".json")
+        os.replace(tmp, path)
+    except OSError as e:  # cache is an optimisation only
+        print("bench: index cache not written (%r)" % (e,), file=sys.stderr)
+
+
+def build_or_load_index(torch, granne_b200, a, dev, elements, seed):
+    """(index handle, index file image, provenance dict).  The image is what both arms search."""
+    path = cache_path(a, elements.shape[0], seed)
+    data, meta = cache_load(path)
+    t0 = time.time()
+    if data is not None:
+        index = granne_b200.Granne.from_device_elements(data, a.kind, elements)
+        return index, data, {"source": "cache", "built_by": meta.get("built_by"), "build_s": meta.get("build_s"),
+                             "load_s": time.time() - t0}
+    b = granne_b200.GranneBuilder.from_device_elements(a.kind, elements, num_neighbors=a.num_neighbors,
+                                                       max_search=200)
+    b.build()
+    build_s = time.time() - t0
+    index = b.get_index()
+    t1 = time.time()
+    data = b.index_bytes()
+    write_s = time.time() - t1
+    b.close()
+    prov = {"source": "built", "built_by": "granne_b200 GPU GranneBuilder", "build_s": build_s,
+            "write_index_s": write_s}
+    cache_store(path, data, prov)
+    return index, data, prov
+
+
+def workload_config(a, impl, n_used, world, prov=None):
     et = "f32" if a.kind == "angular" else "i8"
-    return {"workload": "%dx%d angular %s HNSW (M=%d, build max_search=200), search max_search=%d k=%d, "
-                        "%d queries/step/GPU" % (a.n, a.dim, et, a.num_neighbors, a.max_search, a.k, a.nq),
-            "baseline_config": "BASELINE.json configs[1]" if a.kind == "angular" else "BASELINE.json configs[2] family",
-            "n": a.n, "dim": a.dim, "max_search": a.max_search,
-            "k": a.k, "queries_per_step_per_gpu": a.nq, "index": "replicated, queries sharded" if a.gpus > 1
-            else "single GPU", "l2": "inputs larger than L2 (%.0f MB vectors + adjacency; query batches rotate)"
-            % (a.n * a.dim * (4 if a.kind == "angular" else 1) / 1e6), "streams": a.streams, "impl": impl,
-            "reordered": bool(getattr(a, "reorder", 0))}
+    shards = world if a.mode == "partitioned" else 1
+    return {"workload": "%s%dx%d angular %s HNSW (M=%d, build max_search=200), search max_search=%d k=%d, "
+                        "%d queries/step%s" % ("%d shards x " % shards if shards > 1 or a.mode == "partitioned" else "",
+                                               n_used, a.dim, et, a.num_neighbors, a.max_search, a.k, a.nq,
+                                               "/GPU" if a.mode == "replicated" else " (every shard searches all)"),
+            "baseline_config": a.baseline_config, "requested_n": a.n, "n": n_used, "dim": a.dim,
+            "max_search": a.max_search, "k": a.k, "queries_per_step_per_gpu": a.nq, "mode": a.mode,
+            "distribution": a.dist,
+            "index": ("replicated, queries sharded" if world > 1 else "single GPU") if a.mode == "replicated"
+            else "range-partitioned: one independent index per GPU, merged by (distance, global id)",
+            "index_provenance": dict(prov or {}, shared="both arms search the same granne index file image "
+                                                         "(cached per box)"),
+            "l2": "inputs larger than L2 (%.0f MB vectors + adjacency; query batches rotate)"
+                  % (n_used * a.dim * (4 if a.kind == "angular" else 1) / 1e6), "streams": a.streams, "impl": impl}
 
 
 class ClockSampler:
     """nvidia-smi sampled during the timed region (B200_PROFILING.md clocks line)."""
 
     def __init__(self, gpu_index):
-        self.rows = []
         self.proc = None
         self.gpu = gpu_index
 
@@ -146,13 +300,43 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def cpu_baseline(index_bytes, elements_bytes, queries, a, seconds):
-    """The CPU restatement of the reference (oracle/) on this box's host cores, bounded sample."""
+def pin_to_gpu_numa(local):
+    """Pins this process (and the threads it starts) to the CPUs of the GPU's NUMA node: the e2e path is host-issue
+    bound at 8 ranks x 8 threads, and cross-socket pinned buffers cost latency on every copy."""
+    try:
+        bus = subprocess.run(["nvidia-smi", "-i", str(local), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if bus.startswith("00000000:"):
+            bus = bus[4:]
+        cpus = open("/sys/bus/pci/devices/%s/local_cpulist" % bus).read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            lo, _, hi = part.partition("-")
+            ids.update(range(int(lo), int(hi or lo) + 1))
+        if ids:
+            os.sched_setaffinity(0, ids)
+            return cpus
+    except Exception:
+        pass
+    return None
+
+
+# ---- CPU side (the oracle: test infrastructure, used here only as the timed CPU baseline / reference arm) -------------
+def oracle_index(a, index_bytes, elements_host):
     from oracle import granne_oracle as go
 
+    if a.kind == "angular":
+        el = go.Elements.angular(elements_host, as_is=True)
+    else:
+        el = go.Elements.angular_int(elements_host)
+    g = go.Granne.from_bytes(np.asarray(index_bytes), el)   # compressed adjacency decoded per expansion (faithful)
+    return go, el, g
+
+
+def cpu_baseline(a, index_bytes, elements_host, queries, seconds):
+    """The CPU restatement of the reference (oracle/) on this box's host cores, bounded sample."""
     threads = os.cpu_count() or 1
-    el = go.Elements.from_bytes(a.kind, elements_bytes)
-    g = go.Granne.from_bytes(index_bytes, el)          # compressed adjacency decoded per expansion (faithful)
+    go, el, g = oracle_index(a, index_bytes, elements_host)
     gf = g.to_fixed()                                  # pre-decoded adjacency (the stronger CPU variant)
     probe = queries[:max(threads * 2, 64)]
     t = time.time()
@@ -166,54 +350,106 @@ def cpu_baseline(index_bytes, elements_bytes, queries, a, seconds):
         idx.search_batch(sample, a.max_search, a.k, threads=threads)
         out[name] = nsample / max(time.time() - t, 1e-9)
     best = max(out.values())
-    return {"value": best, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": "%d queries of the bench workload, %d threads, one query per task in static chunks; best of "
-                      "compressed (%.0f QPS) and pre-decoded (%.0f QPS) adjacency" %
+    return {"value": best, "unit": UNIT, "cores": threads,
+            "kind": "port (C++ restatement of the Rust reference; not pinned against a run of the Rust binary: no "
+                    "rustc in the image)",
+            "sample": "%d queries of the bench workload on the SAME index image, %d threads, one query per task in "
+                      "static chunks; best of compressed (%.0f QPS) and pre-decoded (%.0f QPS) adjacency" %
                       (nsample, threads, out["compressed_adjacency"], out["decoded_adjacency"])}
 
 
 def run_reference(a):
-    """Reference arm: the oracle's CPU search (all host threads) on the same configuration; rank 0 only."""
+    """Reference arm: the oracle's CPU search (all host threads) on the same configuration AND the same index image
+    as the ours arm (taken from the box cache; built by the GPU builder as a setup step when the cache is cold — the
+    timed path is the CPU search only).  Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import granne_oracle as go
+    import torch
 
+    import granne_b200
+    from granne_b200 import build as gb_build
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl reference generates the shared synthetic data on the GPU")
+    gb_build.build()
+    granne_b200.load_library()
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
     threads = os.cpu_count() or 1
-    n_centers = max(8, int(4096 * (a.n / 1e6) ** 0.5))
-    raw = clustered(a.n, a.dim, seed=1234, n_centers=n_centers)
-    el = go.Elements.angular(raw) if a.kind == "angular" else go.Elements.angular_int(raw)
-    del raw
-    t0 = time.time()
-    g = go.GranneBuilder(el, num_neighbors=a.num_neighbors, max_search=200).build(threads=threads).to_fixed()
-    build_s = time.time() - t0
-    queries = clustered(a.nq * 16, a.dim, seed=4321, n_centers=n_centers)
-    probe = queries[:max(threads * 2, 64)]
+    world = a.gpus if a.mode == "partitioned" else 1
+    n = a.n
+    while True:
+        try:
+            shards = []
+            t_setup = time.time()
+            for r in range(world):
+                tables = device_tables(torch, dev, a, n)
+                el_dev = make_elements_device(torch, granne_b200, dev, a, n, DATA_SEED + r, tables)
+                index, data, prov = build_or_load_index(torch, granne_b200, a, dev, el_dev, DATA_SEED + r)
+                index.close()
+                host = el_dev.cpu().numpy()
+                del el_dev, index
+                torch.cuda.empty_cache()
+                go, el, g = oracle_index(a, data, host)
+                del host
+                shards.append((el, g, g.to_fixed(), prov))
+            break
+        except (RuntimeError, MemoryError, granne_b200.GranneError) as e:
+            if a.no_fallback or n <= 1_000_000:
+                raise
+            print("bench: reference setup failed at n=%d (%r); retrying with %d" % (n, e, n // 10), file=sys.stderr)
+            n //= 10
+            torch.cuda.empty_cache()
+    tables = device_tables(torch, dev, a, n)
+    pool = 16
+    queries = make_queries_device(torch, dev, a, max(a.nq * pool, 1 << 15), QUERY_SEED, tables).cpu().numpy()
+    setup_s = time.time() - t_setup
+
+    from granne_b200.distributed import merge_topk_host
+
+    def search(qs):
+        if len(shards) == 1:
+            return shards[0][2].search_batch(qs, a.max_search, a.k, threads=threads)
+        parts = [s[2].search_batch(qs, a.max_search, a.k, threads=threads) for s in shards]
+        return merge_topk_host(np.stack([p[0] for p in parts]), np.stack([p[1] for p in parts]),
+                               [r * n for r in range(len(shards))], a.k)
+
+    probe = queries[:max(threads * 4, 256)]
     t = time.time()
-    g.search_batch(probe, a.max_search, a.k, threads=threads)
+    search(probe)
     rate = probe.shape[0] / max(time.time() - t, 1e-6)
-    # bounded sample per step: ~1 s, and at most ~60 s for the whole --steps/--warmup run
-    per_step_s = min(1.0, 60.0 / max(1, a.steps + a.warmup))
-    per_step = int(max(64, min(a.nq, rate * per_step_s)))
-    for _ in range(a.warmup):
-        g.search_batch(queries[:per_step], a.max_search, a.k, threads=threads)
+    # a step must keep every host thread busy (>= 128 queries per thread) yet the whole run must stay bounded
+    per_step_s = min(2.0, 90.0 / max(1, a.steps + a.warmup))
+    per_step = int(max(min(16384, queries.shape[0]), min(queries.shape[0], rate * per_step_s)))
+    per_step = min(per_step, queries.shape[0])
+    for _ in range(min(a.warmup, 3)):
+        search(queries[:per_step])
     t0 = time.time()
     for s in range(a.steps):
-        off = (s * per_step) % (queries.shape[0] - per_step + 1)
-        g.search_batch(queries[off:off + per_step], a.max_search, a.k, threads=threads)
+        off = (s * 4099) % (queries.shape[0] - per_step + 1)
+        search(queries[off:off + per_step])
     dt = time.time() - t0
     qps = a.steps * per_step / dt
+    prov = shards[0][3]
     line = {"metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if a.kind == "angular" else "i8", "data": "synthetic", "impl": "reference", "config": workload_config(a, "reference"),
-            "cpu_baseline": {"value": qps, "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": "%d queries per step (bounded), pre-decoded adjacency, %d threads; index built "
-                                       "by the oracle's threaded builder in %.0f s" % (per_step, threads, build_s)},
+            "dtype": "f32" if a.kind == "angular" else "i8", "data": "synthetic", "impl": "reference",
+            "config": workload_config(a, "reference", n, a.gpus, prov),
+            "cpu_baseline": {"value": qps, "unit": UNIT, "cores": threads,
+                             "kind": "port (C++ restatement of the Rust reference; not pinned against a run of the "
+                                     "Rust binary: no rustc in the image)",
+                             "sample": "%d queries per step (bounded; >= %d per host thread), pre-decoded adjacency, "
+                                       "%d threads (nproc %d), same index image as the ours arm (%s); setup %.0f s"
+                                       % (per_step, per_step // threads, threads, threads, prov.get("source"),
+                                          setup_s)},
             "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
+# ---- the GPU arm -------------------------------------------------------------------------------------------------------
 def main():
     a = parse_args()
     if a.impl == "reference":
@@ -229,6 +465,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the granne_b200 search path has no CPU fallback")
+    cpus = pin_to_gpu_numa(local)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -241,58 +478,80 @@ def main():
     if world > 1:
         dist.barrier()
     granne_b200.load_library()
+    partitioned = a.mode == "partitioned"
+
+    # ---- multi-GPU parity gate: the 2-GPU assertions of tests/multi_gpu_check.py (small oracle-built fixtures, both
+    # modes + the fused gather, bit-compared with the CPU oracle) run before anything is timed
+    parity_checked = None
+    if world > 1:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import multi_gpu_check
+
+        multi_gpu_check.check(rank, world, local, dev)
+        parity_checked = True
 
     # ---- synthetic data, elements, index ---------------------------------------------------------------------------
-    n_centers = max(8, int(4096 * (a.n / 1e6) ** 0.5))
-    t0 = time.time()
-    raw = clustered(a.n, a.dim, seed=1234, n_centers=n_centers)
-    elements_bytes = granne_b200.elements_from_raw(a.kind, raw, device=local)
-    del raw
-    t_data = time.time() - t0
-    t0 = time.time()
-    if rank == 0:
-        builder = granne_b200.GranneBuilder(a.kind, elements_bytes, num_neighbors=a.num_neighbors, max_search=200,
-                                            device=local)
-        builder.build()
-        # very large single-GPU runs skip the host-side file image (only needed for the CPU baseline / replication)
-        big = a.n > 20_000_000 and world == 1
-        index_bytes = None if big else builder.index_bytes()
-        if world == 1:
-            index = builder.get_index()
-        builder_launches = 0
-    t_build = time.time() - t0
-    t_reorder = None
-    if a.reorder and world == 1 and index_bytes is not None:
-        t0 = time.time()
-        index.reorder()
-        t_reorder = time.time() - t0
-        index_bytes = np.frombuffer(index.index_bytes(), dtype=np.uint8)
-        elements_bytes = np.frombuffer(index.elements_bytes(), dtype=np.uint8)
-    if world > 1:
-        size = torch.tensor([len(index_bytes) if rank == 0 else 0], dtype=torch.int64, device=dev)
-        dist.broadcast(size, 0)
-        buf = torch.empty(int(size.item()), dtype=torch.uint8, device=dev)
-        if rank == 0:
-            buf.copy_(torch.from_numpy(np.asarray(index_bytes)))
-        dist.broadcast(buf, 0)
-        index_bytes = buf.cpu().numpy()
-        del buf
-        if rank == 0:
-            builder.close()
-        index = granne_b200.Granne.from_bytes(index_bytes, a.kind, elements_bytes, device=local)
-    elif rank == 0:
-        builder.close()
+    n = a.n
+    t_all = time.time()
+    while True:
+        try:
+            seed = DATA_SEED + (rank if partitioned else 0)
+            t0 = time.time()
+            tables = device_tables(torch, dev, a, n)
+            elements = make_elements_device(torch, granne_b200, dev, a, n, seed, tables)
+            t_data = time.time() - t0
+            t0 = time.time()
+            path = cache_path(a, n, seed)
+            if partitioned or rank == 0 or (path and os.path.exists(path)):
+                index, index_bytes, prov = build_or_load_index(torch, granne_b200, a, dev, elements, seed)
+                ok = 1
+            else:
+                index, index_bytes, prov, ok = None, None, None, 1
+            if world > 1:
+                dist.barrier()          # rank 0 has built and published the image
+                if index is None:
+                    data, meta = cache_load(path)
+                    if data is None:  # no shared cache directory: fall back to a broadcast of the image
+                        ok = 0
+                    else:
+                        index = granne_b200.Granne.from_device_elements(data, a.kind, elements)
+                        index_bytes, prov = data, {"source": "cache", "built_by": meta.get("built_by"),
+                                                   "build_s": meta.get("build_s")}
+                flag = torch.tensor([ok], device=dev)
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+                if int(flag.item()) == 0 and not partitioned:
+                    size = torch.tensor([len(index_bytes) if rank == 0 else 0], dtype=torch.int64, device=dev)
+                    dist.broadcast(size, 0)
+                    buf = torch.empty(int(size.item()), dtype=torch.uint8, device=dev)
+                    if rank == 0:
+                        buf.copy_(torch.from_numpy(np.asarray(index_bytes)))
+                    dist.broadcast(buf, 0)
+                    if index is None:
+                        index_bytes = buf.cpu().numpy()
+                        index = granne_b200.Granne.from_device_elements(index_bytes, a.kind, elements)
+                        prov = {"source": "broadcast from rank 0"}
+                    del buf
+            t_build = time.time() - t0
+            break
+        except (RuntimeError, MemoryError, granne_b200.GranneError) as e:
+            if a.no_fallback or n <= 1_000_000 or world > 1:
+                raise
+            print("bench: setup failed at n=%d (%r); retrying with %d elements" % (n, e, n // 10), file=sys.stderr)
+            n //= 10
+            elements = index = None
+            torch.cuda.empty_cache()
 
     # ---- queries: a rotating pool of distinct batches per rank --------------------------------------------------------
     pool = 16
-    q_host = clustered(a.nq * pool, a.dim, seed=4321 + rank, n_centers=n_centers)
-    q_dev = torch.from_numpy(q_host).to(dev)
+    qseed = QUERY_SEED + (0 if partitioned else rank)      # partitioned: every rank searches the same queries
+    q_dev = make_queries_device(torch, dev, a, a.nq * pool, qseed, tables)
+    q_host = q_dev.cpu().numpy()
     streams = [torch.cuda.Stream(device=dev) for _ in range(max(1, a.streams))]
     # per stream: one int32 buffer [2, nq, k] = ids | distance bits (a single all-gather collects both), + counts
     bufs = [torch.empty((2, a.nq, a.k), dtype=torch.int32, device=dev) for _ in streams]
     outs = [(b[0], b[1].view(torch.float32), torch.empty((a.nq,), dtype=torch.int32, device=dev)) for b in bufs]
     gathered, groups, fused = None, None, None
-    if world > 1 and a.gather == "p2p":
+    if world > 1 and a.gather == "p2p" and not partitioned:
         try:
             from granne_b200.distributed import FusedGather
 
@@ -309,10 +568,15 @@ def main():
         gathered = [torch.empty((world * 2 * a.nq, a.k), dtype=torch.int32, device=dev) for _ in streams]
         # one communicator per stream: collectives of different in-flight steps do not serialise behind each other
         groups = [dist.new_group(backend="nccl") for _ in streams]
+    merged = None
+    if partitioned:
+        from granne_b200.api import merge_topk_device
+
+        bases = [r * n for r in range(world)]
+        merged = [(torch.empty((a.nq, a.k), dtype=torch.int64, device=dev),
+                   torch.empty((a.nq, a.k), dtype=torch.float32, device=dev)) for _ in streams]
 
     qin = [torch.empty((a.nq, a.dim), dtype=torch.float32, device=dev) for _ in streams]
-    graphs = [None] * len(streams)
-
     seq = [0]
 
     def step_body(slot):
@@ -324,30 +588,21 @@ def main():
         index.search_batch_device(qin[slot], a.max_search, a.k, out=outs[slot], stream=streams[slot].cuda_stream)
         if world > 1:  # collect every rank's result tile (NCCL all-gather over NVLink)
             dist.all_gather_into_tensor(gathered[slot], bufs[slot].view(2 * a.nq, a.k), group=groups[slot])
+        if partitioned:  # k-way merge of the per-shard tiles by (distance, global id) on this rank's GPU
+            if world > 1:
+                g = gathered[slot].view(world, 2, a.nq, a.k)
+                part_ids, part_d = g[:, 0].contiguous(), g[:, 1].contiguous().view(torch.float32)
+            else:
+                part_ids, part_d = bufs[slot][0][None], bufs[slot][1][None].view(torch.float32)
+            merge_topk_device(local, part_ids, part_d, bases, out_ids=merged[slot][0], out_dists=merged[slot][1],
+                              stream=streams[slot].cuda_stream)
 
     def device_step(s):
         slot = s % len(streams)
         st = streams[slot]
         with torch.cuda.stream(st):
             qin[slot].copy_(q_dev[(s % pool) * a.nq:(s % pool + 1) * a.nq], non_blocking=True)
-            if graphs[slot] is not None:
-                graphs[slot].replay()
-            else:
-                step_body(slot)
-
-    def capture_graphs():
-        """One CUDA graph per stream slot: search kernels (+ the all-gather) replayed with a single launch."""
-        for slot, st in enumerate(streams):
-            try:
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, stream=st):
-                    step_body(slot)
-                graphs[slot] = g
-            except Exception as e:  # capture unsupported (e.g. NCCL build): fall back to eager launches
-                graphs[slot] = None
-                if rank == 0:
-                    print("cuda graph capture failed, running eagerly: %r" % (e,), file=sys.stderr)
-                break
+            step_body(slot)
 
     def sync_all():
         for st in streams:
@@ -361,20 +616,19 @@ def main():
     index.stream_status()
     st_np = stats.cpu().numpy()
     n_dist, n_expand, n_nbr = st_np[:, 0].mean(), st_np[:, 1].mean(), st_np[:, 2].mean()
+    retried = float((st_np[:, 3] != 0).mean())
     esz = 4 if a.kind == "angular" else 1
     bytes_per_query = n_dist * a.dim * esz + n_nbr * 4 + a.dim * esz  # vectors + adjacency + query
     nsamp = min(256, a.nq)
     if a.kind == "angular":
-        rows = torch.from_numpy(np.frombuffer(elements_bytes, dtype=np.float32, offset=8).reshape(a.n, a.dim))
         qn = torch.nn.functional.normalize(q_dev[:nsamp], dim=1)
     else:  # ground truth under the same i8 angular distance: cosine of the quantised vectors
-        rows = torch.from_numpy(np.frombuffer(elements_bytes, dtype=np.int8, offset=8).reshape(a.n, a.dim))
         qq = q_dev[:nsamp]
         qq = torch.trunc(qq * 127.0 / qq.abs().amax(dim=1, keepdim=True))
         qn = torch.nn.functional.normalize(qq, dim=1)
     best = None
-    for s0 in range(0, a.n, 1 << 18):  # exact brute force in slabs (off the hot path)
-        blk = rows[s0:s0 + (1 << 18)].to(dev)
+    for s0 in range(0, n, 1 << 20):  # exact brute force in slabs over the device-resident elements (off the hot path)
+        blk = elements[s0:s0 + (1 << 20)]
         if a.kind != "angular":
             blk = torch.nn.functional.normalize(blk.float(), dim=1)
         sc = qn @ blk.T
@@ -391,18 +645,18 @@ def main():
     gt = best[1].cpu().numpy()
     got = ids0[:nsamp].cpu().numpy()
     recall = float(np.mean([len(set(gt[i].tolist()) & set(got[i].tolist())) / a.k for i in range(nsamp)]))
-    del rows
+    # the host copy of the elements is only needed by the CPU baseline (rank 0, N = 1)
+    elements_host = None
+    want_cpu = world == 1 and rank == 0 and a.cpu_seconds > 0 and not partitioned
+    if want_cpu:
+        elements_host = elements.cpu().numpy()
+    del elements
+    torch.cuda.empty_cache()
 
     # ---- device-resident timed region ------------------------------------------------------------------------------------
     for s in range(max(a.warmup, len(streams))):
         device_step(s)
     sync_all()
-    if a.graphs and fused is None:
-        capture_graphs()
-        sync_all()
-        for s in range(len(streams)):
-            device_step(s)
-        sync_all()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
@@ -428,14 +682,15 @@ def main():
         dist.barrier()
     torch.cuda.synchronize(dev)
     ms = e0.elapsed_time(e1)
-    launches = index.launch_count() - launches0
+    launches = index.launch_count() - launches0 + (a.steps if partitioned else 0)
     clocks = sampler.stop() if rank == 0 else None
     index.stream_status()
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    value = a.steps * a.nq * world / (ms / 1e3)
+    job_queries = a.steps * a.nq * (1 if partitioned else world)
+    value = job_queries / (ms / 1e3)
 
     # kernel-alone duration (single stream, one launch at a time) for the per-launch roofline
     solo = []
@@ -450,34 +705,61 @@ def main():
     solo_ms = float(np.median(solo[1:]))
 
     # ---- end to end through the public host API ------------------------------------------------------------------------
+    # persistent worker threads (started and parked on a barrier BEFORE t0), each issuing whole batches through
+    # granne_b200_search_batch: memcpy into pinned staging, H2D, kernels, one packed D2H, memcpy out
     nthreads = max(1, min(a.streams, 8))
     h2d = a.nq * a.dim * 4
-    d2h = a.nq * a.k * 8 + a.nq * 4
+    d2h = a.nq * a.k * 8 + a.nq * 4 + 16
 
-    def host_steps(t, count, offset):
-        for s in range(count):
-            b = (offset + s * nthreads + t) % pool
-            index.search_batch(q_host[b * a.nq:(b + 1) * a.nq], a.max_search, a.k)
+    class HostPool:
+        def __init__(self):
+            self.go = threading.Barrier(nthreads + 1)
+            self.done = threading.Barrier(nthreads + 1)
+            self.plan = None
+            self.stop = False
+            self.issue_s = [0.0] * nthreads
+            self.threads = [threading.Thread(target=self.work, args=(t,), daemon=True) for t in range(nthreads)]
+            [t.start() for t in self.threads]
 
-    def run_host(count_total, offset):
-        per = [count_total // nthreads + (1 if t < count_total % nthreads else 0) for t in range(nthreads)]
-        ths = [threading.Thread(target=host_steps, args=(t, per[t], offset)) for t in range(nthreads)]
-        [t.start() for t in ths]
-        [t.join() for t in ths]
+        def work(self, t):
+            while True:
+                self.go.wait()
+                if self.stop:
+                    return
+                count, offset = self.plan
+                mine = count // nthreads + (1 if t < count % nthreads else 0)
+                t0 = time.perf_counter()
+                for s in range(mine):
+                    b = (offset + s * nthreads + t) % pool
+                    index.search_batch(q_host[b * a.nq:(b + 1) * a.nq], a.max_search, a.k)
+                self.issue_s[t] = time.perf_counter() - t0
+                self.done.wait()
 
-    run_host(max(a.warmup, nthreads), 0)
+        def run(self, count, offset):
+            self.plan = (count, offset)
+            self.go.wait()
+            self.done.wait()
+
+        def close(self):
+            self.stop = True
+            self.go.wait()
+
+    hp = HostPool()
+    hp.run(max(a.warmup, 2 * nthreads), 0)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
     t0 = time.perf_counter()
-    run_host(a.steps, 3)
+    hp.run(a.steps, 3)
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
+    e2e_thread_ms = max(hp.issue_s) * 1e3
+    hp.close()
     if world > 1:
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e_qps = a.steps * a.nq * world / e2e_s
+    e2e_qps = job_queries / e2e_s
 
     if rank != 0:
         if world > 1:
@@ -492,37 +774,43 @@ def main():
     tp = os.path.join(ROOT, "profiles", "dram_traffic.json")
     if os.path.exists(tp):
         try:
-            tj = json.load(open(tp))
-            if (tj.get("kind"), tj.get("n"), tj.get("dim"), tj.get("queries_per_launch")) == (a.kind, a.n, a.dim, a.nq):
-                traffic = tj.get("dram_bytes_per_launch")
+            for tj in json.load(open(tp)).get("captures", []):
+                if (tj.get("kind"), tj.get("n"), tj.get("dim"), tj.get("queries_per_launch")) == (a.kind, n, a.dim, a.nq):
+                    traffic = tj.get("dram_bytes_per_launch")
         except Exception:
             traffic = None
     cpu = None
-    if world == 1 and index_bytes is not None and a.cpu_seconds > 0:
-        cpu = cpu_baseline(np.asarray(index_bytes).tobytes(), np.asarray(elements_bytes).tobytes(), q_host, a,
-                           a.cpu_seconds)
+    if want_cpu:
+        cpu = cpu_baseline(a, index_bytes, elements_host, q_host, a.cpu_seconds)
+    kern = {"angular": "DistF32<%d>" % (a.dim // 32), "angular_int": "DistI8"}[a.kind]
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32" if a.kind == "angular" else "i8", "data": "synthetic", "config": workload_config(a, "ours"),
+        "dtype": "f32" if a.kind == "angular" else "i8", "data": "synthetic (generated on the GPU)",
+        "config": workload_config(a, "ours", n, world, prov),
         "recall_at_10": recall,
         "e2e": {"value": e2e_qps, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "host_threads": nthreads, "api": "granne_b200.Granne.search_batch (granne_b200_search_batch)"},
+                "host_threads": nthreads, "host_issue_ms_per_step": e2e_thread_ms / max(1, a.steps / nthreads),
+                "cpu_affinity": cpus, "api": "granne_b200.Granne.search_batch (granne_b200_search_batch)"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src,
-                     "kernel": "search_kernel<%s,7> (1 launch per step)" % ("DistF32<4>" if a.kind == "angular" else "DistI8"),
+                     "traffic": traffic, "traffic_source": "ncu dram__bytes_read+write per launch "
+                                                           "(profiles/dram_traffic.json)" if traffic else None,
+                     "peak_source": peak_src,
+                     "kernel": "search_kernel<%s,7> (1 launch per step; retry + slow passes exit at once)" % kern,
                      "algorithmic_bytes_per_query": bytes_per_query,
                      "algorithmic_bytes_per_launch": bytes_per_query * a.nq,
                      "n_dist_per_query": n_dist, "n_expand_per_query": n_expand,
+                     "queries_beyond_fast_pass": retried,
                      "solo_launch_ms": solo_ms,
                      "solo_launch_gbs": bytes_per_query * a.nq / (solo_ms / 1e3) / 1e9},
         "cpu_baseline": cpu,
-        "setup_s": {"data+elements": t_data, "gpu_index_build": t_build, "reorder": t_reorder},
-        "host_issue_ms_per_step": issue_ms / a.steps, "cuda_graphs": bool(graphs[0] is not None),
-        "multi_gpu_gather": None if world == 1 else ("p2p peer stores fused into the search kernels" if fused is not None
-                                                     else "nccl all_gather"),
+        "parity_checked": parity_checked,
+        "setup_s": {"data+elements": t_data, "index(build or load)": t_build, "total": time.time() - t_all},
+        "host_issue_ms_per_step": issue_ms / a.steps,
+        "multi_gpu_gather": None if world == 1 else ("nccl all_gather + merge_topk_kernel" if partitioned else (
+            "p2p peer stores fused into the search kernels" if fused is not None else "nccl all_gather")),
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -43,6 +43,9 @@ def load_library():
         "granne_b200_last_error": (C.c_char_p, []),
         "granne_b200_open": (i32, [vp, sz, i32, vp, sz, vp, sz, i32, C.POINTER(vp)]),
         "granne_b200_open_files": (i32, [C.c_char_p, i32, C.c_char_p, C.c_char_p, i32, C.POINTER(vp)]),
+        "granne_b200_open_device_elements": (i32, [vp, sz, i32, vp, u64, u32, i32, C.POINTER(vp)]),
+        "granne_b200_builder_new_device_elements": (i32, [vp, i32, vp, u64, u32, i32, C.POINTER(vp)]),
+        "granne_b200_elements_from_raw_device": (i32, [i32, vp, u64, u32, i32, vp, vp]),
         "granne_b200_close": (None, [vp]),
         "granne_b200_len": (u64, [vp]),
         "granne_b200_num_layers": (u64, [vp]),
@@ -149,6 +152,28 @@ class Granne:
         self.device = device
         self._elements_src = ("bytes", elements_bytes)
         self._embeddings_src = ("bytes", embeddings_bytes) if embeddings_bytes is not None else None
+        return self
+
+    @classmethod
+    def from_device_elements(cls, index_bytes, element_type, elements, device=None):
+        """Granne::from_bytes with a device-resident element container: `elements` is a contiguous CUDA torch tensor
+        [n, dim] of ELEMENTS (normalised float32 for "angular", int8 for "angular_int") on the target device — e.g.
+        the output of elements_from_raw_device.  Nothing bounces through the host (100M x 128 f32 = 51 GB)."""
+        L = load_library()
+        kind = _kind(element_type)
+        _check_device_rows(kind, elements)
+        device = elements.device.index if device is None else device
+        if elements.device.index != device:
+            raise ValueError("elements tensor lives on cuda:%d, not cuda:%d" % (elements.device.index, device))
+        self = cls.__new__(cls)
+        h = C.c_void_p()
+        ib = np.frombuffer(index_bytes, dtype=np.uint8)
+        _check(L.granne_b200_open_device_elements(_ptr(ib), ib.size, kind, C.c_void_p(elements.data_ptr()),
+                                                  elements.shape[0], elements.shape[1], device, C.byref(h)))
+        self._h = h
+        self.device = device
+        self._elements_src = None
+        self._embeddings_src = None
         return self
 
     @staticmethod
@@ -336,9 +361,18 @@ class Granne:
         (ids int32 view of u32 bits, dists float32, counts int32).  Asynchronous on the current torch stream."""
         import torch
 
-        q = queries
+        q = self._check_device_queries(queries)
         fmt = QUERY_ELEMENT if already_element or q.dtype == torch.int8 else QUERY_RAW_F32
         nq, k = q.shape[0], int(num_elements)
+        if out is not None:
+            for t, dt, shape in zip(out, (torch.int32, torch.float32, torch.int32), ((nq, k), (nq, k), (nq,))):
+                if (not t.is_cuda or t.device != q.device or t.dtype != dt or tuple(t.shape) != shape
+                        or not t.is_contiguous()):
+                    raise ValueError("out tensors must be contiguous (ids int32 [nq,k], dists float32 [nq,k], counts "
+                                     "int32 [nq]) on the queries' device")
+        if stats is not None and (not stats.is_cuda or stats.device != q.device or stats.dtype != torch.int64
+                                  or tuple(stats.shape) != (nq, STATS_PER_QUERY) or not stats.is_contiguous()):
+            raise ValueError("stats must be a contiguous int64 [nq, %d] tensor on the queries' device" % STATS_PER_QUERY)
         if out is None:
             dev = q.device
             out = (torch.empty((nq, k), dtype=torch.int32, device=dev),
@@ -358,12 +392,30 @@ class Granne:
         gathered buffer described by `gather` (a PeerGather)."""
         import torch
 
-        q = queries
+        q = self._check_device_queries(queries)
         fmt = QUERY_ELEMENT if already_element or q.dtype == torch.int8 else QUERY_RAW_F32
         s = stream if stream is not None else torch.cuda.current_stream(q.device).cuda_stream
         _check(load_library().granne_b200_search_batch_device_gather(
             self._h, C.c_void_p(q.data_ptr()), q.shape[0], fmt, int(max_search), int(num_elements), C.byref(gather),
             C.c_void_p(counts.data_ptr()) if counts is not None else None, None, C.c_void_p(s)))
+
+    def _check_device_queries(self, q):
+        """Same checks as the host path (search_batch): a wrong dtype, width, device or a strided view would make the
+        kernels read out of bounds (they index queries as qi * dim)."""
+        import torch
+
+        if not isinstance(q, torch.Tensor) or not q.is_cuda:
+            raise ValueError("queries must be a CUDA torch tensor")
+        if q.device.index != self.device:
+            raise ValueError("queries live on cuda:%s, the index on cuda:%d" % (q.device.index, self.device))
+        if q.dim() != 2 or q.shape[1] != self.dim:
+            raise ValueError("queries must have shape (nq, %d)" % self.dim)
+        if q.dtype == torch.int8:
+            if self.element_kind != ANGULAR_INT:
+                raise ValueError("int8 queries need an angular_int index")
+        elif q.dtype != torch.float32:
+            raise ValueError("queries must be float32 (or int8 elements for angular_int)")
+        return q.contiguous()
 
     def stream_status(self):
         _check(load_library().granne_b200_stream_status(self._h))
@@ -403,6 +455,37 @@ def elements_from_raw(element_type, raw, device=0):
     return out
 
 
+def _check_device_rows(kind, t):
+    import torch
+
+    want = torch.int8 if kind == ANGULAR_INT else torch.float32
+    if kind not in (ANGULAR, ANGULAR_INT):
+        raise ValueError("device-resident elements: angular or angular_int")
+    if not isinstance(t, torch.Tensor) or not t.is_cuda or t.dim() != 2 or t.dtype != want or not t.is_contiguous():
+        raise ValueError("elements must be a contiguous CUDA tensor [n, dim] of %s" % want)
+
+
+def elements_from_raw_device(element_type, raw, out=None, stream=None):
+    """`Vector::from(Vec<f32>)` per row, device to device: raw = CUDA float32 [n, dim]; returns (or fills `out`) the
+    elements as a CUDA tensor [n, dim] (float32 normalised for "angular", int8 for "angular_int")."""
+    import torch
+
+    kind = _kind(element_type)
+    if not raw.is_cuda or raw.dtype != torch.float32 or raw.dim() != 2 or not raw.is_contiguous():
+        raise ValueError("raw must be a contiguous CUDA float32 tensor [n, dim]")
+    n, dim = raw.shape
+    if out is None:
+        out = torch.empty((n, dim), dtype=torch.int8 if kind == ANGULAR_INT else torch.float32, device=raw.device)
+    _check_device_rows(kind, out)
+    if tuple(out.shape) != (n, dim) or out.device != raw.device:
+        raise ValueError("out must match raw's shape and device")
+    s = stream if stream is not None else torch.cuda.current_stream(raw.device).cuda_stream
+    _check(load_library().granne_b200_elements_from_raw_device(kind, C.c_void_p(raw.data_ptr()), n, dim,
+                                                               raw.device.index, C.c_void_p(out.data_ptr()),
+                                                               C.c_void_p(s)))
+    return out
+
+
 class GranneBuilder:
     """granne.GranneBuilder (py/src/lib.rs:346-579; src/index/mod.rs:295-531) on the GPU.
 
@@ -435,6 +518,33 @@ class GranneBuilder:
         self._embeddings_bytes = embeddings_bytes
         self._pending = []
 
+    @classmethod
+    def from_device_elements(cls, element_type, elements, num_neighbors=30, max_search=200, layer_multiplier=15.0,
+                             reinsert_elements=True, expected_num_elements=None, device=None):
+        """GranneBuilder::new(config, elements) over a device-resident container (see Granne.from_device_elements)."""
+        L = load_library()
+        kind = _kind(element_type)
+        _check_device_rows(kind, elements)
+        device = elements.device.index if device is None else device
+        cfg = BuildConfig()
+        L.granne_b200_build_config_default(C.byref(cfg))
+        cfg.num_neighbors = num_neighbors
+        cfg.max_search = max_search
+        cfg.layer_multiplier = layer_multiplier
+        cfg.reinsert_elements = int(bool(reinsert_elements))
+        cfg.expected_num_elements = -1 if expected_num_elements is None else int(expected_num_elements)
+        self = cls.__new__(cls)
+        h = C.c_void_p()
+        _check(L.granne_b200_builder_new_device_elements(C.byref(cfg), kind, C.c_void_p(elements.data_ptr()),
+                                                         elements.shape[0], elements.shape[1], device, C.byref(h)))
+        self._h = h
+        self.device = device
+        self._element_type = element_type
+        self._elements_bytes = None
+        self._embeddings_bytes = None
+        self._pending = []
+        return self
+
     def append(self, element):
         """GranneBuilder.append(element) (py/src/lib.rs:474-476; py/src/variants/builder.rs:6-21): the raw vector
         becomes an element (`Vector::from`) and is pushed; it is indexed by the next build().  Rows are buffered and
@@ -450,8 +560,9 @@ class GranneBuilder:
         self._pending = []
         image = elements_from_raw(self._element_type, raw, self.device)
         _check(load_library().granne_b200_builder_append(self._h, _ptr(image), image.size))
-        old = np.frombuffer(self._elements_bytes, dtype=np.uint8)
-        self._elements_bytes = np.concatenate([old, image[8:]])  # same u64 width prefix, more rows
+        if self._elements_bytes is not None:
+            old = np.frombuffer(self._elements_bytes, dtype=np.uint8)
+            self._elements_bytes = np.concatenate([old, image[8:]])  # same u64 width prefix, more rows
 
     def build(self, num_elements=0):
         """Builder::build() / build_partial(num_elements)."""
@@ -489,13 +600,15 @@ class GranneBuilder:
         g = Granne.__new__(Granne)
         g._h = h
         g.device = self.device
-        g._elements_src = ("bytes", self._elements_bytes)
+        g._elements_src = ("bytes", self._elements_bytes) if self._elements_bytes is not None else None
         g._embeddings_src = ("bytes", self._embeddings_bytes) if self._embeddings_bytes is not None else None
         return g
 
     def save_elements(self, path):
         """GranneBuilder.save_elements(path) (py/src/lib.rs:518-522)."""
         self._flush()
+        if self._elements_bytes is None:
+            raise GranneError(-1, "this builder was made from device-resident elements: no host image to save")
         with open(path, "wb") as f:
             f.write(bytes(self._elements_bytes))
 

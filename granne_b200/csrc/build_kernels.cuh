@@ -171,7 +171,7 @@ __device__ __forceinline__ void setup_ctx(const DeviceIndex& ix, WarpCtx& c, Lin
     c.lane = threadIdx.x;
     unsigned char* sp = smem_raw;
     c.tile = reinterpret_cast<float*>(sp);
-    c.ids = reinterpret_cast<uint32_t*>(sp + tile_rows * kTileStride * sizeof(float));
+    c.ids = reinterpret_cast<uint32_t*>(sp + tile_bytes_for_rows(tile_rows) - kIdScratchBytes);
     sp += tile_bytes_for_rows(tile_rows);
     c.bar = smem_u32(sp);
     c.phase = 0;

@@ -12,9 +12,37 @@
 #include <cstdint>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace granne_b200 {
+
+// Splits [0, n) into contiguous ranges, one per worker thread (large layers: 100M nodes decode/encode in seconds
+// instead of minutes).  fn(begin, end, worker).  Small inputs run inline.
+template <class F>
+inline void parallel_ranges(uint64_t n, F&& fn, uint64_t min_per_thread = 1u << 16) {
+    unsigned hw = std::thread::hardware_concurrency();
+    if (hw == 0) hw = 1;
+    uint64_t t = std::min<uint64_t>(std::min<unsigned>(hw, 32u), n / min_per_thread);
+    if (t <= 1) {
+        fn((uint64_t)0, n, 0u);
+        return;
+    }
+    std::vector<std::thread> th;
+    const uint64_t per = (n + t - 1) / t;
+    for (uint64_t w = 0; w < t; ++w) {
+        const uint64_t b = w * per, e = std::min(n, b + per);
+        if (b >= e) break;
+        th.emplace_back([&fn, b, e, w] { fn(b, e, (unsigned)w); });
+    }
+    for (auto& x : th) x.join();
+}
+inline unsigned parallel_workers(uint64_t n, uint64_t min_per_thread = 1u << 16) {
+    unsigned hw = std::thread::hardware_concurrency();
+    if (hw == 0) hw = 1;
+    const uint64_t t = std::min<uint64_t>(std::min<unsigned>(hw, 32u), n / min_per_thread);
+    return t <= 1 ? 1u : (unsigned)t;
+}
 
 constexpr uint32_t kUnused = 0xFFFFFFFFu;   // NeighborId::max_value(), src/index/mod.rs:27-28
 constexpr size_t kMetadataLen = 1024;       // src/index/io.rs:7
@@ -190,35 +218,60 @@ inline bool decode_layer(const uint8_t* blob, size_t len, HostLayer* layer, std:
     const uint64_t n = offsets.empty() ? 0 : offsets.size() - 1;
 
     // pass 1: degrees (count byte of each entry)
+    const unsigned workers = parallel_workers(n);
+    std::vector<uint32_t> wmax(workers, 0);
+    std::vector<int> wbad(workers, 0);
+    parallel_ranges(n, [&](uint64_t b, uint64_t e, unsigned w) {
+        uint32_t mx = 0;
+        for (uint64_t i = b; i < e; ++i) {
+            if (offsets[i] >= offsets[i + 1] || offsets[i + 1] > data_len) {
+                wbad[w] = 1;
+                return;
+            }
+            const uint32_t cnt = data[offsets[i]];
+            if (cnt > mx) mx = cnt;
+        }
+        wmax[w] = mx;
+    });
     uint32_t max_deg = 0;
-    for (uint64_t i = 0; i < n; ++i) {
-        if (offsets[i] >= offsets[i + 1] || offsets[i + 1] > data_len) {
+    for (unsigned w = 0; w < workers; ++w) {
+        if (wbad[w]) {
             *err = "neighbour list offsets out of range";
             return false;
         }
-        const uint32_t cnt = data[offsets[i]];
-        if (cnt > max_deg) max_deg = cnt;
+        max_deg = std::max(max_deg, wmax[w]);
     }
     layer->num_nodes = n;
     layer->max_degree = max_deg;
     layer->width = ((max_deg < 1 ? 1 : max_deg) + 7u) & ~7u;
-    layer->rows.assign(static_cast<size_t>(n) * layer->width, kUnused);
-    uint32_t tmp[256];
-    for (uint64_t i = 0; i < n; ++i) {
-        uint32_t cnt = 0;
-        if (!decode_neighbor_list(data + offsets[i], static_cast<size_t>(offsets[i + 1] - offsets[i]), tmp, &cnt)) {
-            *err = "garbled neighbour list";
+    layer->rows.resize(static_cast<size_t>(n) * layer->width);
+    const uint32_t width = layer->width;
+    uint32_t* all_rows = layer->rows.data();
+    // pass 2: decode every list into its fixed-width row (padding written in the same pass)
+    parallel_ranges(n, [&](uint64_t b, uint64_t e, unsigned w) {
+        uint32_t tmp[256];
+        for (uint64_t i = b; i < e; ++i) {
+            uint32_t cnt = 0;
+            if (!decode_neighbor_list(data + offsets[i], static_cast<size_t>(offsets[i + 1] - offsets[i]), tmp, &cnt)) {
+                wbad[w] = 1;
+                return;
+            }
+            uint32_t* row = all_rows + static_cast<size_t>(i) * width;
+            for (uint32_t k = 0; k < cnt; ++k) {
+                if (tmp[k] == kUnused) {
+                    wbad[w] = 2;
+                    return;
+                }
+                row[k] = tmp[k];
+            }
+            for (uint32_t k = cnt; k < width; ++k) row[k] = kUnused;
+        }
+    });
+    for (unsigned w = 0; w < workers; ++w)
+        if (wbad[w]) {
+            *err = wbad[w] == 2 ? "neighbour id 0xFFFFFFFF is reserved" : "garbled neighbour list";
             return false;
         }
-        uint32_t* row = &layer->rows[static_cast<size_t>(i) * layer->width];
-        for (uint32_t k = 0; k < cnt; ++k) {
-            if (tmp[k] == kUnused) {
-                *err = "neighbour id 0xFFFFFFFF is reserved";
-                return false;
-            }
-            row[k] = tmp[k];
-        }
-    }
     return true;
 }
 
@@ -267,8 +320,20 @@ inline bool parse_index(const uint8_t* buf, size_t len, HostGraph* graph, std::s
             *err = "layers must grow monotonically";
             return false;
         }
-        for (uint32_t v : L.rows)
-            if (v != kUnused && v >= L.num_nodes) {
+        const uint64_t total = L.rows.size();
+        const unsigned workers = parallel_workers(total, 1u << 20);
+        std::vector<int> bad(workers, 0);
+        const uint32_t* rp = L.rows.data();
+        const uint64_t nn = L.num_nodes;
+        parallel_ranges(total, [&](uint64_t b, uint64_t e, unsigned w) {
+            for (uint64_t i = b; i < e; ++i)
+                if (rp[i] != kUnused && rp[i] >= nn) {
+                    bad[w] = 1;
+                    return;
+                }
+        }, 1u << 20);
+        for (unsigned w = 0; w < workers; ++w)
+            if (bad[w]) {
                 *err = "neighbour id out of range in layer " + std::to_string(l);
                 return false;
             }
@@ -375,21 +440,29 @@ inline bool encode_layer(const uint32_t* rows, uint64_t num_nodes, uint32_t stri
     const size_t base = out->size();
     out->resize(base + 8 + bytes_for_offsets, 0xFF);
     for (int b = 0; b < 8; ++b) (*out)[base + b] = static_cast<uint8_t>(static_cast<uint64_t>(bytes_for_offsets) >> (8 * b));
-    std::vector<uint64_t> offsets;
-    offsets.reserve(num_nodes + 1);
-    offsets.push_back(0);
-    std::vector<uint32_t> tmp;
-    uint64_t total = 0;
-    for (uint64_t i = 0; i < num_nodes; ++i) {
-        tmp.clear();
-        const uint32_t* row = rows + i * stride;
-        for (uint32_t k = 0; k < stride; ++k)
-            if (row[k] != kUnused) tmp.push_back(row[k]);  // predicate |&x| x != UNUSED (io.rs:33)
-        std::sort(tmp.begin(), tmp.end());
-        const size_t before = out->size();
-        encode_neighbor_list(tmp.data(), static_cast<uint32_t>(tmp.size()), out);
-        total += out->size() - before;
-        offsets.push_back(total);
+    // every worker encodes a contiguous node range into its own buffer; the buffers are concatenated in order
+    std::vector<uint64_t> offsets(num_nodes + 1, 0);  // offsets[i + 1] = encoded size of node i, prefix-summed below
+    const unsigned workers = parallel_workers(num_nodes);
+    std::vector<std::vector<uint8_t>> parts(workers);
+    parallel_ranges(num_nodes, [&](uint64_t b, uint64_t e, unsigned w) {
+        std::vector<uint8_t>& buf = parts[w];
+        buf.reserve((e - b) * (stride + 8));
+        std::vector<uint32_t> tmp;
+        for (uint64_t i = b; i < e; ++i) {
+            tmp.clear();
+            const uint32_t* row = rows + i * stride;
+            for (uint32_t k = 0; k < stride; ++k)
+                if (row[k] != kUnused) tmp.push_back(row[k]);  // predicate |&x| x != UNUSED (io.rs:33)
+            std::sort(tmp.begin(), tmp.end());
+            const size_t before = buf.size();
+            encode_neighbor_list(tmp.data(), static_cast<uint32_t>(tmp.size()), &buf);
+            offsets[i + 1] = buf.size() - before;
+        }
+    });
+    for (uint64_t i = 0; i < num_nodes; ++i) offsets[i + 1] += offsets[i];
+    for (unsigned w = 0; w < workers; ++w) {
+        out->insert(out->end(), parts[w].begin(), parts[w].end());
+        std::vector<uint8_t>().swap(parts[w]);
     }
     // Offsets::push: chunks of 60 u16 deltas with a u64 `initial` (offsets.rs:148-241)
     uint8_t* chunks = out->data() + base + 8;

@@ -125,7 +125,8 @@ int dev_alloc(Handle* h, T** out, size_t count) {
 }
 
 // Uploads `nrows` dense rows in slabs through a temporary device buffer and re-lays them out on the device.
-int stage_dense(Handle* h, const uint8_t* host_rows, uint64_t nrows, uint32_t dim, bool is_i8) {
+int stage_dense(Handle* h, const uint8_t* host_rows, uint64_t nrows, uint32_t dim, bool is_i8,
+                bool device_src = false) {
     gb::DeviceIndex& d = h->dev;
     d.dim = dim;
     d.full = dim / 32;
@@ -140,16 +141,20 @@ int stage_dense(Handle* h, const uint8_t* host_rows, uint64_t nrows, uint32_t di
         d.vectors = dst;
         const uint64_t slab = std::max<uint64_t>(1, (64ull << 20) / dim);
         int8_t* tmp = nullptr;
-        GB_CUDA(cudaMalloc(&tmp, (size_t)std::min(slab, std::max<uint64_t>(nrows, 1)) * dim));
+        if (!device_src) GB_CUDA(cudaMalloc(&tmp, (size_t)std::min(slab, std::max<uint64_t>(nrows, 1)) * dim));
         for (uint64_t r0 = 0; r0 < nrows; r0 += slab) {
             const uint64_t nr = std::min(slab, nrows - r0);
-            GB_CUDA(cudaMemcpy(tmp, host_rows + r0 * dim, (size_t)nr * dim, cudaMemcpyHostToDevice));
-            gb::pad_rows_i8_kernel<<<h->num_sms * 8, 256>>>(tmp, dst + r0 * d.row_stride, nr, dim, d.row_stride);
+            const int8_t* src = reinterpret_cast<const int8_t*>(host_rows) + r0 * dim;  // device memory if device_src
+            if (!device_src) {
+                GB_CUDA(cudaMemcpy(tmp, src, (size_t)nr * dim, cudaMemcpyHostToDevice));
+                src = tmp;
+            }
+            gb::pad_rows_i8_kernel<<<h->num_sms * 8, 256>>>(src, dst + r0 * d.row_stride, nr, dim, d.row_stride);
             h->launches++;
             GB_CUDA(cudaGetLastError());
         }
         GB_CUDA(cudaDeviceSynchronize());
-        GB_CUDA(cudaFree(tmp));
+        if (tmp) GB_CUDA(cudaFree(tmp));
     } else {
         const uint32_t full = d.full;
         const bool templated = (full <= 4 || full == 6 || full == 8) && h->dev.kind == gb::kAngularF32;
@@ -161,18 +166,22 @@ int stage_dense(Handle* h, const uint8_t* host_rows, uint64_t nrows, uint32_t di
         d.vectors = dst;
         const uint64_t slab = std::max<uint64_t>(1, (64ull << 20) / (dim * 4ull));
         float* tmp = nullptr;
-        GB_CUDA(cudaMalloc(&tmp, (size_t)std::min(slab, std::max<uint64_t>(nrows, 1)) * dim * 4));
-        const float* src = reinterpret_cast<const float*>(host_rows);
+        if (!device_src) GB_CUDA(cudaMalloc(&tmp, (size_t)std::min(slab, std::max<uint64_t>(nrows, 1)) * dim * 4));
+        const float* src = reinterpret_cast<const float*>(host_rows);  // device memory if device_src
         for (uint64_t r0 = 0; r0 < nrows; r0 += slab) {
             const uint64_t nr = std::min(slab, nrows - r0);
-            GB_CUDA(cudaMemcpy(tmp, src + r0 * dim, (size_t)nr * dim * 4, cudaMemcpyHostToDevice));
-            gb::permute_rows_f32_kernel<<<h->num_sms * 8, 256>>>(tmp, dst + r0 * d.row_stride, nr, dim, full,
+            const float* from = src + r0 * dim;
+            if (!device_src) {
+                GB_CUDA(cudaMemcpy(tmp, from, (size_t)nr * dim * 4, cudaMemcpyHostToDevice));
+                from = tmp;
+            }
+            gb::permute_rows_f32_kernel<<<h->num_sms * 8, 256>>>(from, dst + r0 * d.row_stride, nr, dim, full,
                                                                  d.vec_group, d.row_stride);
             h->launches++;
             GB_CUDA(cudaGetLastError());
         }
         GB_CUDA(cudaDeviceSynchronize());
-        GB_CUDA(cudaFree(tmp));
+        if (tmp) GB_CUDA(cudaFree(tmp));
     }
     return GRANNE_B200_OK;
 }
@@ -215,6 +224,25 @@ int stage_elements(Handle* h, int kind, const uint8_t* el, size_t el_len, const 
     return GRANNE_B200_OK;
 }
 
+// Stages a dense element container whose rows already live in HBM (row-major elements: normalised f32 / i8).
+int stage_device_elements(Handle* h, int kind, const void* d_rows, uint64_t n, uint32_t dim) {
+    if (kind != GRANNE_B200_ANGULAR && kind != GRANNE_B200_ANGULAR_INT)
+        return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "device-resident elements: angular or angular_int only");
+    if (!d_rows && n) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "elements pointer is null");
+    if (dim == 0 || dim > 16384) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "vectors wider than 16384 are unsupported");
+    cudaPointerAttributes at{};
+    if (n && (cudaPointerGetAttributes(&at, d_rows) != cudaSuccess || at.type != cudaMemoryTypeDevice ||
+              at.device != h->device)) {
+        cudaGetLastError();
+        return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "elements pointer is not device memory of the requested device");
+    }
+    h->dev.kind = kind;
+    int rc = stage_dense(h, static_cast<const uint8_t*>(d_rows), n, dim, kind == GRANNE_B200_ANGULAR_INT, true);
+    if (rc) return rc;
+    h->dev.num_elements = n;
+    return GRANNE_B200_OK;
+}
+
 int check_open_args(const void* el, int kind, const void* emb) {
     if (!el) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "elements buffer is null");
     if (kind != GRANNE_B200_ANGULAR && kind != GRANNE_B200_ANGULAR_INT && kind != GRANNE_B200_EMBEDDINGS)
@@ -231,12 +259,14 @@ void finish_handle(Handle* h) {
     h->slow_vis_slots = (uint32_t)std::min<uint64_t>(want, 16ull << 20);
 }
 
+// `dev_rows` != nullptr: the element container is given as device-resident rows (n_dev x dim_dev) instead of a file image
 int open_impl(const uint8_t* index_bytes, size_t index_len, int kind, const uint8_t* el, size_t el_len,
-              const uint8_t* emb, size_t emb_len, int device, Handle** out) {
+              const uint8_t* emb, size_t emb_len, int device, Handle** out, const void* dev_rows = nullptr,
+              uint64_t n_dev = 0, uint32_t dim_dev = 0) {
     if (!out) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "out handle pointer is null");
     *out = nullptr;
     if (!index_bytes) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "index buffer is null");
-    int rc = check_open_args(el, kind, emb);
+    int rc = dev_rows ? GRANNE_B200_OK : check_open_args(el, kind, emb);
     if (rc) return rc;
 
     std::unique_ptr<Handle> h(new Handle());
@@ -249,7 +279,11 @@ int open_impl(const uint8_t* index_bytes, size_t index_len, int kind, const uint
     gb::HostGraph graph;
     if (!gb::parse_index(index_bytes, index_len, &graph, &err)) return fail(GRANNE_B200_ERR_FORMAT, err);
     if (graph.layers.size() > (size_t)gb::kMaxLayers) return fail(GRANNE_B200_ERR_FORMAT, "too many layers");
-    if ((rc = stage_elements(h.get(), kind, el, el_len, emb, emb_len))) return rc;
+    if (dev_rows)
+        rc = stage_device_elements(h.get(), kind, dev_rows, n_dev, dim_dev);
+    else
+        rc = stage_elements(h.get(), kind, el, el_len, emb, emb_len);
+    if (rc) return rc;
 
     gb::DeviceIndex& d = h->dev;
     d.num_layers = (int)graph.layers.size();
@@ -887,6 +921,18 @@ int granne_b200_open(const void* index_bytes, size_t index_len, int element_kind
     }
 }
 
+int granne_b200_open_device_elements(const void* index_bytes, size_t index_len, int element_kind,
+                                     const void* d_element_rows, uint64_t num_elements, uint32_t dim, int device,
+                                     granne_b200_index** out) {
+    try {
+        if (!d_element_rows) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "elements pointer is null");
+        return open_impl(static_cast<const uint8_t*>(index_bytes), index_len, element_kind, nullptr, 0, nullptr, 0,
+                         device, out, d_element_rows, num_elements, dim);
+    } catch (const std::exception& e) {
+        return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, std::string("exception: ") + e.what());
+    }
+}
+
 int granne_b200_open_files(const char* index_path, int element_kind, const char* elements_path,
                            const char* embeddings_path, int device, granne_b200_index** out) {
     try {
@@ -1128,13 +1174,13 @@ void granne_b200_build_config_default(granne_b200_build_config* cfg) {
     cfg->show_progress = 0;
 }
 
-int granne_b200_builder_new(const granne_b200_build_config* cfg, int element_kind, const void* elements_bytes,
+static int builder_new_impl(const granne_b200_build_config* cfg, int element_kind, const void* elements_bytes,
                             size_t elements_len, const void* embeddings_bytes, size_t embeddings_len, int device,
-                            granne_b200_builder** out) {
+                            granne_b200_builder** out, const void* dev_rows, uint64_t n_dev, uint32_t dim_dev) {
     try {
         if (!out || !cfg) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "null argument");
         *out = nullptr;
-        int rc = check_open_args(elements_bytes, element_kind, embeddings_bytes);
+        int rc = dev_rows ? GRANNE_B200_OK : check_open_args(elements_bytes, element_kind, embeddings_bytes);
         if (rc) return rc;
         if (cfg->num_neighbors < 1 || cfg->num_neighbors > 31)
             return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "num_neighbors must be in 1..31 for the GPU builder");
@@ -1150,8 +1196,11 @@ int granne_b200_builder_new(const granne_b200_build_config* cfg, int element_kin
         if (rc) return rc;
         h->device = device;
         GB_CUDA(cudaSetDevice(device));
-        rc = stage_elements(h, element_kind, static_cast<const uint8_t*>(elements_bytes), elements_len,
-                            static_cast<const uint8_t*>(embeddings_bytes), embeddings_len);
+        if (dev_rows)
+            rc = stage_device_elements(h, element_kind, dev_rows, n_dev, dim_dev);
+        else
+            rc = stage_elements(h, element_kind, static_cast<const uint8_t*>(elements_bytes), elements_len,
+                                static_cast<const uint8_t*>(embeddings_bytes), embeddings_len);
         if (rc) return rc;
         if (h->dev.num_elements >= 0xFFFFFFFFull)  // assert!(elements.len() < UNUSED) (:420)
             return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "too many elements");
@@ -1164,6 +1213,20 @@ int granne_b200_builder_new(const granne_b200_build_config* cfg, int element_kin
     } catch (const std::exception& e) {
         return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, std::string("exception: ") + e.what());
     }
+}
+
+int granne_b200_builder_new(const granne_b200_build_config* cfg, int element_kind, const void* elements_bytes,
+                            size_t elements_len, const void* embeddings_bytes, size_t embeddings_len, int device,
+                            granne_b200_builder** out) {
+    return builder_new_impl(cfg, element_kind, elements_bytes, elements_len, embeddings_bytes, embeddings_len, device,
+                            out, nullptr, 0, 0);
+}
+
+int granne_b200_builder_new_device_elements(const granne_b200_build_config* cfg, int element_kind,
+                                            const void* d_element_rows, uint64_t num_elements, uint32_t dim,
+                                            int device, granne_b200_builder** out) {
+    if (!d_element_rows) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "elements pointer is null");
+    return builder_new_impl(cfg, element_kind, nullptr, 0, nullptr, 0, device, out, d_element_rows, num_elements, dim);
 }
 
 // GranneBuilder::push for the dense containers (ExtendableElementContainer::push, src/index/mod.rs:512-531;
@@ -1369,6 +1432,26 @@ int granne_b200_elements_from_raw(int element_kind, const float* raw, uint64_t n
     cudaFree(d_raw);
     cudaFree(d_out);
     return rc;
+}
+
+// Vector::from per row (angular.rs:55-61 / angular_int.rs:28-45), device to device: d_raw = n x dim f32 rows in HBM,
+// d_out = n x dim elements (f32 or i8), both on `device`; runs on `cuda_stream` (asynchronous).
+int granne_b200_elements_from_raw_device(int element_kind, const float* d_raw, uint64_t n, uint32_t dim, int device,
+                                         void* d_out, void* cuda_stream) {
+    if (element_kind != GRANNE_B200_ANGULAR && element_kind != GRANNE_B200_ANGULAR_INT)
+        return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "elements_from_raw supports angular and angular_int");
+    if (dim == 0 || dim > 12000) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "unsupported dimension");
+    if (n == 0) return GRANNE_B200_OK;
+    if (!d_raw || !d_out) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "null argument");
+    int sms = 0;
+    size_t optin = 0;
+    int rc = check_device(device, &sms, &optin);
+    if (rc) return rc;
+    GB_CUDA(cudaSetDevice(device));
+    gb::make_elements_kernel<<<(unsigned)std::min<uint64_t>(n, (uint64_t)sms * 32), 32, (size_t)dim * 4,
+                               static_cast<cudaStream_t>(cuda_stream)>>>(d_raw, n, dim, element_kind, d_out);
+    GB_CUDA(cudaGetLastError());
+    return GRANNE_B200_OK;
 }
 
 // ---- compute_distance (py/src/lib.rs:71-89) -----------------------------------------------------------------------

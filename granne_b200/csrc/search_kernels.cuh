@@ -51,9 +51,13 @@ constexpr unsigned long long kFlagExpanded = 1ull << 63;
 constexpr unsigned long long kKeyMask = ~kFlagExpanded;
 constexpr unsigned kFullMask = 0xFFFFFFFFu;
 constexpr int kTileStride = 36;  // floats per tile row: 16-byte aligned rows, conflict-free LDS.128 per quarter warp
-// 32 x u32 compacted candidate ids | 32 x (id, distance bits) keys of a merge | 2 x 32 u32 speculative adjacency rows
-constexpr int kIdScratchBytes = 640;
-__host__ __device__ constexpr uint32_t tile_bytes_for_rows(uint32_t rows) { return rows * kTileStride * 4u + kIdScratchBytes; }
+// per-warp scratch behind the tile: 32 x u32 compacted candidate ids | 2 x 32 u32 speculative adjacency rows |
+// 32 x 16-byte speculative visited buckets.  The 32 x (id, distance bits) keys of a merge are parked in the tile itself
+// (idle outside the distance phase), which is therefore at least 256 bytes.
+constexpr int kIdScratchBytes = 896;
+__host__ __device__ constexpr uint32_t tile_bytes_for_rows(uint32_t rows) {
+    return (rows * kTileStride * 4u < 256u ? 256u : rows * kTileStride * 4u) + kIdScratchBytes;
+}
 
 enum ElementKind : int { kAngularF32 = 0, kAngularI8 = 1, kSumEmbeddings = 2 };
 enum QueryFormat : int { kQueryRawF32 = 0, kQueryElement = 1, kQueryById = 2 };  // ById: builder only (u32 ids)
@@ -339,7 +343,8 @@ struct DistF32 {
     // Gather: one cp.async per row (per 32-chunk group): lane l copies the V*4 bytes of the permuted row that lane l
     // itself consumes, so a row costs SHFL + address + LDGSTS, all rows of the batch are in flight together, no data
     // registers are held and no cross-lane barrier is needed before the partial sums.
-    __device__ __forceinline__ float dists(const DeviceIndex& ix, WarpCtx& c, uint32_t my_id, int k) {
+    template <class Hook>
+    __device__ __forceinline__ float dists(const DeviceIndex& ix, WarpCtx& c, uint32_t my_id, int k, Hook&& after_wait) {
         float d = 0.0f;
         if (FULL > 0) {
             const uint32_t stride_bytes = ix.row_stride * 4u;
@@ -363,6 +368,7 @@ struct DistF32 {
                                                        src + g * 32 * lane_bytes);
                 }
                 cp_async_wait_all();
+                if (j0 == 0) after_wait();  // everything copied before this call has landed too
 #pragma unroll
                 for (int b = 0; b < 8; ++b) {
                     if (b >= nb) break;
@@ -373,16 +379,24 @@ struct DistF32 {
                 if (has_tail) id = __shfl_sync(kFullMask, my_id, (j0 + c.lane) & 31);  // lane t: candidate j0 + t
                 float db = 0.0f;
                 if (c.lane < nb) db = ordered_finish(ix, c, id, c.lane);
-                // hand the distance of candidate j0 + t (computed by lane t) to lane j0 + t
-                const float dj = __shfl_sync(kFullMask, db, (c.lane - j0) & 31);
-                if (c.lane >= j0 && c.lane < j0 + nb) d = dj;
+                if (j0 == 0) {
+                    d = db;  // first batch: lane t already is candidate t
+                } else {
+                    // hand the distance of candidate j0 + t (computed by lane t) to lane j0 + t
+                    const float dj = __shfl_sync(kFullMask, db, (c.lane - j0) & 31);
+                    if (c.lane >= j0 && c.lane < j0 + nb) d = dj;
+                }
                 __syncwarp();  // the next batch rewrites the tile
             }
         } else {
             if (c.lane < k) d = ordered_finish(ix, c, my_id, 0);
             __syncwarp();
+            after_wait();
         }
         return d;
+    }
+    __device__ __forceinline__ float dists(const DeviceIndex& ix, WarpCtx& c, uint32_t my_id, int k) {
+        return dists(ix, c, my_id, k, [] {});
     }
 };
 
@@ -391,6 +405,12 @@ struct DistF32Generic {
     static constexpr bool kStaged = false;
     static constexpr bool kMbar = false;
     __device__ __forceinline__ void load_query(const DeviceIndex&, const WarpCtx&) {}
+    template <class Hook>
+    __device__ __forceinline__ float dists(const DeviceIndex& ix, WarpCtx& c, uint32_t my_id, int k, Hook&& after_wait) {
+        const float d = dists(ix, c, my_id, k);
+        after_wait();
+        return d;
+    }
     __device__ __forceinline__ float dists(const DeviceIndex& ix, WarpCtx& c, uint32_t my_id, int k) {
         const float* base = static_cast<const float*>(ix.vectors);
         const size_t stride = ix.row_stride;
@@ -427,6 +447,12 @@ struct DistI8 {
     static constexpr bool kStaged = true;
     static constexpr bool kMbar = true;
     __device__ __forceinline__ void load_query(const DeviceIndex&, const WarpCtx&) {}
+    template <class Hook>
+    __device__ __forceinline__ float dists(const DeviceIndex& ix, WarpCtx& c, uint32_t my_id, int k, Hook&& after_wait) {
+        const float d = dists(ix, c, my_id, k);
+        after_wait();
+        return d;
+    }
     __device__ __forceinline__ float dists(const DeviceIndex& ix, WarpCtx& c, uint32_t my_id, int k) {
         const uint32_t stride = ix.row_stride;
         const int words = stride / 4;
@@ -535,6 +561,12 @@ struct DistSum {
     // lane partials of the two dot products (norm, distance) go through the 8-row tile so that the strictly ordered
     // 32-lane sums of a whole batch run in parallel (lane b sums candidate b) instead of two 32-step shuffle chains
     // per candidate.
+    template <class Hook>
+    __device__ __forceinline__ float dists(const DeviceIndex& ix, WarpCtx& c, uint32_t my_id, int k, Hook&& after_wait) {
+        const float d = dists(ix, c, my_id, k);
+        after_wait();
+        return d;
+    }
     __device__ __forceinline__ float dists(const DeviceIndex& ix, WarpCtx& c, uint32_t my_id, int k) {
         const float* emb = static_cast<const float*>(ix.vectors);
         const size_t stride = ix.row_stride;
@@ -645,13 +677,20 @@ __device__ __forceinline__ void stcg_u4(uint4* p, uint4 v, unsigned long long po
                  : "memory");
 }
 constexpr uint32_t kVisHashMul = 0x9E3779B1u;
+// `pre` (warp-uniform, may be null): shared-memory copy of the home buckets of this very row, taken after the last
+// insertion into the table (speculative expansion, see search_layer_fast) — it replaces the first round's loads.
 __device__ __forceinline__ bool vis_bucket_insert(uint32_t* tab, uint32_t nbuckets, uint32_t id, bool valid,
-                                                  bool* overflow, unsigned long long policy) {
+                                                  bool* overflow, unsigned long long policy,
+                                                  const uint4* pre = nullptr) {
     uint32_t b = __umulhi(id * kVisHashMul, nbuckets);
     bool pending = valid, is_new = false;
     for (int probe = 0;; ++probe) {
         uint32_t* bucket = tab + (size_t)b * 4u;
-        const uint4 v = ldcg_u4(bucket, policy);
+        uint4 v;
+        if (probe == 0 && pre != nullptr)
+            v = pre[threadIdx.x];
+        else
+            v = ldcg_u4(bucket, policy);
         const bool found = (v.x == id) | (v.y == id) | (v.z == id) | (v.w == id);
         pending = pending && !found;
         // slots are filled in order: the bucket is full iff its last slot is used
@@ -969,7 +1008,9 @@ __device__ __forceinline__ void search_layer_fast(const DeviceIndex& ix, WarpCtx
     }
     uint32_t n = 1, n_exp = 0, cursor = 0, pos_thr = 0, thr_bits = 0;
     uint32_t spec_id = kUnusedId, spec_slot = 0;
-    uint32_t* const spec_rows = c.ids + 96;
+    bool spec_bk = false;  // the speculative row's home buckets were copied (valid until the next insertion)
+    uint32_t* const spec_rows = c.ids + 32;
+    uint4* const spec_buckets = reinterpret_cast<uint4*>(c.ids + 96);
 
     while (true) {
         // ---- pq.pop(): first unexpanded entry at or after the cursor; also find the runner-up ----
@@ -995,8 +1036,10 @@ __device__ __forceinline__ void search_layer_fast(const DeviceIndex& ix, WarpCtx
         // wait on the same scoreboard as the load issued here.)  Every pop commits exactly one — possibly empty —
         // group, so "all groups but the last" at the consumer is precisely the previous pop's row.
         const bool have_cur = (spec_id == xid) && (width <= 32u);
+        const bool have_bk = have_cur && spec_bk;
         const uint32_t* cur_row = spec_rows + 32u * spec_slot;
         spec_id = kUnusedId;
+        spec_bk = false;
         {
             const unsigned rest = sel_mask & (sel_mask - 1);
             if (rest && width <= 32u) {
@@ -1055,7 +1098,8 @@ __device__ __forceinline__ void search_layer_fast(const DeviceIndex& ix, WarpCtx
             if (vm == 0) break;
             c.n_nbr += __popc(vm);
             bool ovf = false;
-            const bool is_new = vis_bucket_insert(c.visited, nbuckets, nb, valid, &ovf, c.pol_keep);
+            const bool is_new = vis_bucket_insert(c.visited, nbuckets, nb, valid, &ovf, c.pol_keep,
+                                                  have_bk ? spec_buckets : nullptr);
             const unsigned nm = __ballot_sync(kFullMask, is_new);
             const int k = __popc(nm);
             vis_count += k;
@@ -1069,21 +1113,26 @@ __device__ __forceinline__ void search_layer_fast(const DeviceIndex& ix, WarpCtx
             __syncwarp();
             const uint32_t my_id = c.ids[lane < k ? lane : 0];
             c.n_dist += k;
-            const float d = dist.dists(ix, c, my_id, k);
+            // While this expansion's candidate rows are in flight the speculative adjacency row lands too; as soon as
+            // the wait is over (inside dists) its neighbours' home buckets are copied from the visited table into
+            // shared memory, so that a correct guess finds them there instead of paying an L2 round trip.  The
+            // copies are issued after this expansion's insertions and no insertion follows before they are used.
+            const float d = dist.dists(ix, c, my_id, k, [&] {
+                if (spec_id != kUnusedId) {
+                    cp_async_wait_all();
+                    const uint32_t sn = ((uint32_t)lane < width) ? spec_rows[32u * spec_slot + lane] : kUnusedId;
+                    cp_async_lane<16>(smem_u32(spec_buckets + lane),
+                                      c.visited + (size_t)__umulhi(sn * kVisHashMul, nbuckets) * 4u);
+                    cp_async_commit();  // its own group: the consumer waits for all groups but the next pop's
+                    spec_bk = true;
+                }
+            });
             if (__any_sync(kFullMask, c.status & kStatusNotFinite)) {
                 c.status |= kStatusNotFinite;
                 *out_n = n;
                 return;
             }
             const uint32_t my_d = __float_as_uint(d);
-            // The speculative row arrived with this expansion's candidate rows (same cp.async wait): warm L2 with
-            // the visited buckets of its neighbours.
-            if (spec_id != kUnusedId && (uint32_t)lane < width) {
-                const uint32_t sn = spec_rows[32u * spec_slot + lane];
-                if (sn != kUnusedId)
-                    asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(
-                        c.visited + (size_t)__umulhi(sn * kVisHashMul, nbuckets) * 4u));
-            }
             // !res.is_full() || distance < res.peek().0   (:1029)
             bool pass = (lane < k) && (n_exp < ef || my_d < thr_bits);
             // a key strictly farther than the last entry of a full list has >= ef strictly closer entries before
@@ -1094,7 +1143,7 @@ __device__ __forceinline__ void search_layer_fast(const DeviceIndex& ix, WarpCtx
             const uint32_t m = __popc(pm);
 
             // park the passing keys (compacted) in shared memory: key t = (id, distance bits) as one 64-bit word
-            uint2* keys = reinterpret_cast<uint2*>(c.ids + 32);
+            uint2* keys = reinterpret_cast<uint2*>(c.tile);
             if (pass) keys[__popc(pm & lt)] = make_uint2(my_id, my_d);
             // rank of my key among the entries: branch-free lower bound on the distance over the padded array
             // (entries at positions >= n are sentinels), refined by id on exact distance ties
@@ -1349,7 +1398,7 @@ __global__ void __launch_bounds__(32, R > 0 ? GB_MIN_BLOCKS : 1) search_kernel(c
     //                                                          ... | list | visited (generic pass, slow_pass == 0)
     unsigned char* sp = smem_raw;
     c.tile = reinterpret_cast<float*>(sp);
-    c.ids = reinterpret_cast<uint32_t*>(sp + a.tile_rows * kTileStride * sizeof(float));
+    c.ids = reinterpret_cast<uint32_t*>(sp + tile_bytes_for_rows(a.tile_rows) - kIdScratchBytes);
     sp += tile_bytes_for_rows(a.tile_rows);
     c.bar = smem_u32(sp);
     c.phase = 0;

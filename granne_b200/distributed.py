@@ -176,7 +176,7 @@ class PartitionedGranne:
     """One independent index per contiguous id range (one per rank); all queries searched on every shard; per-shard
     tiles all-gathered and merged by (distance, global id)."""
 
-    def __init__(self, index=None, shard_base=0, group=None, local_search=None, device_index=0, host_merge=False):
+    def __init__(self, index=None, shard_base=0, group=None, local_search=None, device_index=None, host_merge=False):
         import torch
         import torch.distributed as dist
 
@@ -215,7 +215,10 @@ class PartitionedGranne:
         if all_ids.is_cuda:
             from .api import merge_topk_device
 
-            return merge_topk_device(self.device_index, all_ids, all_d, self.bases)
+            # merge on the device the tiles live on (one process per GPU: that is this rank's device, whatever
+            # ordinal the caller's default device has)
+            dev = all_ids.device.index if self.device_index is None else self.device_index
+            return merge_topk_device(dev, all_ids, all_d, self.bases)
         if not self.host_merge:
             raise RuntimeError("PartitionedGranne merges on the GPU; CPU tensors are only accepted with "
                                "host_merge=True (host-logic tests over gloo)")

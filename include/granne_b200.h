@@ -210,6 +210,11 @@ typedef struct granne_b200_builder granne_b200_builder;
 int granne_b200_builder_new(const granne_b200_build_config* cfg, int element_kind, const void* elements_bytes,
                             size_t elements_len, const void* embeddings_bytes, size_t embeddings_len, int device,
                             granne_b200_builder** out);
+/* GranneBuilder::new(config, elements) with the element container given as device rows (see "device-resident element
+ * containers" below: row-major elements, num_elements x dim, memory of `device`). */
+int granne_b200_builder_new_device_elements(const granne_b200_build_config* cfg, int element_kind,
+                                            const void* d_element_rows, uint64_t num_elements, uint32_t dim,
+                                            int device, granne_b200_builder** out);
 /* GranneBuilder::push (src/index/mod.rs:512-531; py GranneBuilder.append, py/src/lib.rs:474-476) for the angular and
  * angular_int containers: appends the rows of an elements file image (same width) to the builder's container; they are
  * indexed by the next build.  Not concurrent with other calls on `b`. */
@@ -238,6 +243,23 @@ void granne_b200_builder_free(granne_b200_builder* b);
  * Call with out == NULL to query the size. */
 int granne_b200_elements_from_raw(int element_kind, const float* raw, uint64_t n, uint32_t dim, int device, void* out,
                                   size_t cap, size_t* out_len);
+
+/* ---- device-resident element containers ---------------------------------------------------------------------------
+ * The reference borrows its element container from the caller (`Vectors::from_slice`, src/elements/dense_vector.rs:
+ * 66-72; `Granne::from_bytes(index, &elements)`, src/index/mod.rs:108-113).  When the rows are already in HBM (made
+ * by another kernel, or too large to bounce through the host: 100M x 128 f32 = 51 GB) these variants take them as a
+ * device pointer: row-major ELEMENTS (normalised f32 for ANGULAR, i8 for ANGULAR_INT), num_elements x dim, memory of
+ * `device`.  The rows are copied into the staged layout during the call; the caller keeps its buffer. */
+
+/* Vector::from per row (angular.rs:55-61 / angular_int.rs:28-45), device to device, asynchronous on `cuda_stream`:
+ * d_raw = n x dim raw f32 rows, d_out = n x dim elements (f32 or i8). */
+int granne_b200_elements_from_raw_device(int element_kind, const float* d_raw, uint64_t n, uint32_t dim, int device,
+                                         void* d_out, void* cuda_stream);
+
+/* Granne::from_bytes (src/index/mod.rs:108-113) with the element container given as device rows. */
+int granne_b200_open_device_elements(const void* index_bytes, size_t index_len, int element_kind,
+                                     const void* d_element_rows, uint64_t num_elements, uint32_t dim, int device,
+                                     granne_b200_index** out);
 
 /* compute_distance (py/src/lib.rs:71-89) for n pairs: out[i] = Vector::from(a_i).dist(&Vector::from(b_i)) for
  * GRANNE_B200_ANGULAR (src/elements/angular.rs:55-74) or GRANNE_B200_ANGULAR_INT (angular_int.rs:19-59); `a`, `b` are

@@ -27,6 +27,14 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
+    check(rank, world, local, dev)
+    if rank == 0:
+        print("multi-gpu check ok: world=%d replicated + partitioned parity" % world)
+    dist.destroy_process_group()
+
+
+def check(rank, world, local, dev):
+    """The assertions proper, on an initialised NCCL process group (bench.py runs them before every N > 1 timing)."""
     granne_b200.load_library()
     q = random_vectors(1000, 32, seed=77)
     tq = torch.from_numpy(q).to(dev)
@@ -64,7 +72,7 @@ def main():
     el2, g2, ib2, eb2, _ = build_fixture(go, "angular", sizes[rank], 32, seed=100 + rank, num_neighbors=10,
                                          max_search=50)
     shard = granne_b200.Granne.from_bytes(ib2, "angular", eb2, device=local)
-    part = PartitionedGranne(shard, shard_base=bases[rank], device_index=local)
+    part = PartitionedGranne(shard, shard_base=bases[rank])
     gi, gd = part.search_batch(tq, 50, 10)
     torch.cuda.synchronize()
     assert part.bases == bases
@@ -76,9 +84,8 @@ def main():
     assert np.array_equal(gi.cpu().numpy(), ei), "partitioned ids"
     assert np.array_equal(gd.cpu().numpy().view(np.uint32), ed.view(np.uint32)), "partitioned dists"
     dist.barrier()
-    if rank == 0:
-        print("multi-gpu check ok: world=%d replicated + partitioned parity" % world)
-    dist.destroy_process_group()
+    shard.close()
+    idx.close()
 
 
 if __name__ == "__main__":
