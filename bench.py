@@ -246,48 +246,60 @@ def workload_config(a, impl, n_used, world, prov=None):
 
 
 class ClockSampler:
-    """nvidia-smi sampled during the timed region (B200_PROFILING.md clocks line)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line).  The timed
+    region is a few milliseconds to a few hundred, so the samples come from NVML in-process (about every 0.5 ms) rather
+    than from an nvidia-smi subprocess (100 ms period: it would miss the region)."""
 
-    def __init__(self, gpu_index):
-        self.proc = None
-        self.gpu = gpu_index
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def __init__(self, torch, gpu_index):
+        self.rows, self.bits, self.thread, self.h, self.nv = [], 0, None, None, None
+        self.running = False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            p = torch.cuda.get_device_properties(gpu_index)
+            try:
+                bus = "%08x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+                self.h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.nv = pynvml
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.h = None
+
+    def _loop(self):
+        nv, h = self.nv, self.h
+        reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(
+            nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while self.running:
+            try:
+                self.rows.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                self.bits |= int(reasons(h))
+            except Exception:
+                break
+            time.sleep(0.0003)
 
     def start(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        except OSError:
-            self.proc = None
+        if self.h is None:
+            return
+        self.old_interval = sys.getswitchinterval()
+        sys.setswitchinterval(0.0002)  # let the sampler run between the launches the main thread issues
+        self.running = True
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            out, _ = self.proc.communicate(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-            out, _ = self.proc.communicate()
-        sm, mx, reasons = [], [], set()
-        for line in out.strip().splitlines():
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        if self.h is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvml unavailable"]}
+        self.running = False
+        self.thread.join()
+        sys.setswitchinterval(self.old_interval)
+        return {"sm_mhz": float(np.median(self.rows)) if self.rows else None, "sm_max_mhz": self.max_mhz,
+                "samples": len(self.rows), "source": "nvml, sampled inside the timed region",
+                "reasons": sorted(name for bit, name in self.REASONS.items() if self.bits & bit)}
 
 
 def measured_peak_gbs():
@@ -321,6 +333,28 @@ def pin_to_gpu_numa(local):
     return None
 
 
+def spread_over_all_cores():
+    """The CPU arms get the whole host: every logical CPU, and memory interleaved over all NUMA nodes (a search thread
+    gathers random rows of a 51 GB array: with first-touch placement half of the threads would read remote memory)."""
+    ncpu = os.cpu_count() or 1
+    try:
+        os.sched_setaffinity(0, range(ncpu))
+    except OSError:
+        pass
+    try:
+        import ctypes
+
+        nodes = len([d for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()])
+        if nodes > 1:
+            mask = ctypes.c_ulong((1 << nodes) - 1)
+            libc = ctypes.CDLL(None, use_errno=True)
+            libc.syscall(238, 3, ctypes.byref(mask), 65)  # set_mempolicy(MPOL_INTERLEAVE, all nodes)
+            return "interleaved over %d NUMA nodes" % nodes
+    except Exception:
+        pass
+    return "default placement"
+
+
 # ---- CPU side (the oracle: test infrastructure, used here only as the timed CPU baseline / reference arm) -------------
 def oracle_index(a, index_bytes, elements_host):
     from oracle import granne_oracle as go
@@ -336,6 +370,7 @@ def oracle_index(a, index_bytes, elements_host):
 def cpu_baseline(a, index_bytes, elements_host, queries, seconds):
     """The CPU restatement of the reference (oracle/) on this box's host cores, bounded sample."""
     threads = os.cpu_count() or 1
+    placement = spread_over_all_cores()
     go, el, g = oracle_index(a, index_bytes, elements_host)
     gf = g.to_fixed()                                  # pre-decoded adjacency (the stronger CPU variant)
     probe = queries[:max(threads * 2, 64)]
@@ -354,8 +389,8 @@ def cpu_baseline(a, index_bytes, elements_host, queries, seconds):
             "kind": "port (C++ restatement of the Rust reference; not pinned against a run of the Rust binary: no "
                     "rustc in the image)",
             "sample": "%d queries of the bench workload on the SAME index image, %d threads, one query per task in "
-                      "static chunks; best of compressed (%.0f QPS) and pre-decoded (%.0f QPS) adjacency" %
-                      (nsample, threads, out["compressed_adjacency"], out["decoded_adjacency"])}
+                      "static chunks, memory %s; best of compressed (%.0f QPS) and pre-decoded (%.0f QPS) adjacency" %
+                      (nsample, threads, placement, out["compressed_adjacency"], out["decoded_adjacency"])}
 
 
 def run_reference(a):
@@ -378,6 +413,7 @@ def run_reference(a):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     threads = os.cpu_count() or 1
+    placement = spread_over_all_cores()
     world = a.gpus if a.mode == "partitioned" else 1
     n = a.n
     while True:
@@ -441,9 +477,9 @@ def run_reference(a):
                              "kind": "port (C++ restatement of the Rust reference; not pinned against a run of the "
                                      "Rust binary: no rustc in the image)",
                              "sample": "%d queries per step (bounded; >= %d per host thread), pre-decoded adjacency, "
-                                       "%d threads (nproc %d), same index image as the ours arm (%s); setup %.0f s"
-                                       % (per_step, per_step // threads, threads, threads, prov.get("source"),
-                                          setup_s)},
+                                       "%d threads (nproc %d), memory %s, same index image as the ours arm (%s); "
+                                       "setup %.0f s" % (per_step, per_step // threads, threads, threads, placement,
+                                                         prov.get("source"), setup_s)},
             "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -660,7 +696,7 @@ def main():
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(torch, local)
     if rank == 0:
         sampler.start()
     launches0 = index.launch_count()

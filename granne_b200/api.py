@@ -188,12 +188,8 @@ class Granne:
 
     def index_bytes(self):
         """Index::write_index (src/index/io.rs:11-70) into memory, from the staged graph."""
-        L = load_library()
-        need = C.c_size_t()
-        _check(L.granne_b200_write_index(self._h, None, 0, C.byref(need)))
-        out = np.empty(need.value, dtype=np.uint8)
-        _check(L.granne_b200_write_index(self._h, _ptr(out), out.size, C.byref(need)))
-        return out[:need.value].tobytes()
+        return _write_index(load_library().granne_b200_write_index, self._h,
+                            [self.layer_len(l) for l in range(self.num_layers())]).tobytes()
 
     def elements_bytes(self):
         """The elements file image (u64 dim + rows, src/slice_vector/mod.rs:460-466; offsets + 3-byte ids for
@@ -455,6 +451,20 @@ def elements_from_raw(element_type, raw, device=0):
     return out
 
 
+def _write_index(fn, handle, layer_lens):
+    """One encode instead of two: the first call gets a buffer sized for the common case (<= 32 neighbours per node:
+    1 count byte + 4 bytes per id is the writer's worst case); only an index with wider rows needs the size query."""
+    guess = 1024 + sum(8 + (1 + n // 60) * 128 + n * (1 + 4 * 32) for n in layer_lens)
+    out = np.empty(guess, dtype=np.uint8)
+    need = C.c_size_t()
+    rc = fn(handle, _ptr(out), out.size, C.byref(need))
+    if rc != 0 and need.value > out.size:
+        out = np.empty(need.value, dtype=np.uint8)
+        rc = fn(handle, _ptr(out), out.size, C.byref(need))
+    _check(rc)
+    return out[:need.value]
+
+
 def _check_device_rows(kind, t):
     import torch
 
@@ -579,13 +589,9 @@ class GranneBuilder:
         return int(load_library().granne_b200_builder_layer_len(self._h, layer))
 
     def index_bytes(self):
-        """Index::write_index into memory: a granne index file image."""
-        L = load_library()
-        need = C.c_size_t()
-        _check(L.granne_b200_builder_write_index(self._h, None, 0, C.byref(need)))
-        out = np.empty(need.value, dtype=np.uint8)
-        _check(L.granne_b200_builder_write_index(self._h, _ptr(out), out.size, C.byref(need)))
-        return out[:need.value]
+        """Index::write_index into memory: a granne index file image (uint8 array)."""
+        return _write_index(load_library().granne_b200_builder_write_index, self._h,
+                            [self.layer_len(l) for l in range(self.num_layers())])
 
     def save_index(self, path):
         """GranneBuilder.save_index(path) (py/src/lib.rs)."""

@@ -357,7 +357,10 @@ inline bool parse_dense(const uint8_t* buf, size_t len, size_t scalar_bytes, Den
     }
     const uint64_t width = load_le(buf, 8);
     const size_t payload = len - 8;
-    if (width == 0 || payload % (width * scalar_bytes) != 0) {  // assert!(width > 0 && data.len() % width == 0)
+    // assert!(width > 0 && data.len() % width == 0); a width beyond the payload is rejected BEFORE multiplying
+    // (width * scalar_bytes must not wrap: 2^62 * 4 == 0 would divide by zero)
+    if (width == 0 || width > payload / scalar_bytes + 1 || width > (1ull << 40) ||
+        payload % (width * scalar_bytes) != 0) {
         *err = "elements file: width must be > 0 and divide the payload";
         return false;
     }

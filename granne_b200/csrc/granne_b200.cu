@@ -43,6 +43,25 @@ int fail(int code, const std::string& msg) {
         }                                                                                               \
     } while (0)
 
+// Every entry point runs on its handle's device and leaves the caller's current device as it found it (a host
+// application — e.g. one torch process per GPU — must not see its default device change under it).
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        err = cudaSetDevice(device);
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define GB_DEVICE(device)          \
+    DeviceGuard _device_guard(device); \
+    GB_CUDA(_device_guard.err)
+
 // Per-call scratch: device copies of queries/results, status words, stream.  Pooled per handle so that several host
 // threads can search concurrently (the reference's `search` is `&self` and reentrant).
 struct Workspace {
@@ -56,8 +75,13 @@ struct Workspace {
     size_t out_cap_q = 0, out_cap_k = 0;
     int* d_status = nullptr;  // nq ints
     size_t status_cap = 0;
-    unsigned int* d_counters = nullptr;  // [0]=fast work counter, [1]=slow work counter
-    int* d_error = nullptr;              // [0]=sticky error bits of this call, [1]=overflow seen
+    // one 64-byte block, zeroed once per call: [0..2] work counters of the three passes, [3] fast pass flagged
+    // something, [4] retry pass flagged something, [5] done counter (fused gather); d_error = words [8..11]
+    unsigned int* d_counters = nullptr;
+    int* d_error = nullptr;              // [0]=sticky error bits of this call (inside the counters block)
+    unsigned long long* d_retried = nullptr;  // cumulative: queries that needed more than the fast pass
+    unsigned long long* h_retried = nullptr;  // pinned mirror (copied at the end of every call, read without a sync)
+    unsigned long long seen_retried = 0, seen_total = 0, total_queries = 0;
     void* h_pinned = nullptr;            // staging for host<->device copies
     size_t pinned_cap = 0;
     // slow path
@@ -67,6 +91,9 @@ struct Workspace {
     // fast pass: per-CTA visited tables in global memory
     uint32_t* d_vis = nullptr;
     size_t vis_cap = 0;  // u32 entries
+    // retry pass: fewer CTAs, larger tables
+    uint32_t* d_vis_retry = nullptr;
+    size_t vis_retry_cap = 0;
 };
 
 }  // namespace
@@ -85,6 +112,9 @@ struct granne_b200_index {
     std::mutex pool_mu;
     std::vector<std::unique_ptr<Workspace>> pool;                     // host-pointer API: one per concurrent call
     std::map<cudaStream_t, std::unique_ptr<Workspace>> stream_ws;     // device-pointer API: one per caller stream
+    // fast-pass visited tables are sized max_search x degree x vis_scale; the scale doubles (up to 8) when more than
+    // 1% of the recent queries overflowed into the retry pass (heavier data distributions visit more nodes)
+    std::atomic<uint32_t> vis_scale{1};
     // slow path sizing
     uint32_t slow_ctas = 4;
     uint32_t slow_list_cap = 32768;
@@ -134,7 +164,7 @@ int stage_dense(Handle* h, const uint8_t* host_rows, uint64_t nrows, uint32_t di
     d.num_vectors = nrows;
     if (is_i8) {
         d.vec_group = 1;
-        d.row_stride = (dim + 15u) & ~15u;
+        d.row_stride = (dim + 31u) & ~31u;  // rows start on 32-byte sector boundaries (DistI8)
         int8_t* dst = nullptr;
         int rc = dev_alloc(h, &dst, (size_t)nrows * d.row_stride);
         if (rc) return rc;
@@ -273,7 +303,7 @@ int open_impl(const uint8_t* index_bytes, size_t index_len, int kind, const uint
     rc = check_device(device, &h->num_sms, &h->smem_optin);
     if (rc) return rc;
     h->device = device;
-    GB_CUDA(cudaSetDevice(device));
+    GB_DEVICE(device);
 
     std::string err;
     gb::HostGraph graph;
@@ -348,7 +378,7 @@ LaunchPlan make_plan(const Handle* h, uint32_t max_search) {
     p.list_cap = p.rows ? 32u * p.rows : std::max<uint32_t>(32, (max_search + 16 + 31) & ~31u);
     const uint32_t deg = h->layer_max_degree.empty() ? 1 : std::max<uint32_t>(8, h->layer_max_degree.back());
     uint64_t want = std::max<uint64_t>(1024, (uint64_t)max_search * std::min<uint32_t>(deg, 64));
-    want = (want + 31) & ~31ull;
+    want = ((want + 31) & ~31ull) * h->vis_scale.load();
     const uint32_t qbytes = (d.kind == gb::kAngularI8) ? d.row_stride : ((d.dim + 3u) & ~3u) * 4u;
     p.staged = is_staged_kind(d);
     p.tile_rows = d.kind == gb::kAngularI8 ? 0u : ((p.staged || d.kind == gb::kSumEmbeddings) ? 8u : 32u);
@@ -361,11 +391,15 @@ LaunchPlan make_plan(const Handle* h, uint32_t max_search) {
         p.stg_rows = std::min<uint32_t>(8u, std::max<uint32_t>(4, (8192u / p.stg_row_bytes) & ~3u));
         base = ((base + 127) & ~size_t(127)) + (size_t)p.stg_rows * p.stg_row_bytes;
     }
-    if (p.staged) {
-        const uint32_t row_bytes = d.kind == gb::kAngularI8 ? d.row_stride : d.full * 128u;
+    if (p.staged && d.kind == gb::kAngularI8) {
+        // DistI8: the staging tile is a set of 512-byte pass slots (32 lanes x one 16-byte chunk each)
+        p.stg_row_bytes = 512;
+        p.stg_rows = std::max<uint32_t>(2, (unsigned)GB_STG_BYTES / 512u);
+        base = ((base + 127) & ~size_t(127)) + (size_t)p.stg_rows * p.stg_row_bytes;
+    } else if (p.staged) {
+        const uint32_t row_bytes = d.full * 128u;
         p.stg_row_bytes = row_bytes;
-        p.stg_rows = std::min<uint32_t>(d.kind == gb::kAngularI8 ? 16u : 8u,
-                                        std::max<uint32_t>(4, ((unsigned)GB_STG_BYTES / row_bytes) & ~3u));
+        p.stg_rows = std::min<uint32_t>(8u, std::max<uint32_t>(4, ((unsigned)GB_STG_BYTES / row_bytes) & ~3u));
         base = ((base + 127) & ~size_t(127)) + (size_t)p.stg_rows * row_bytes;
     }
     p.base_smem = base;
@@ -390,17 +424,31 @@ LaunchPlan make_plan(const Handle* h, uint32_t max_search) {
     return p;
 }
 
-template <class Dist, int R>
-int launch_kernels(Handle* h, Workspace* w, gb::SearchArgs a, const LaunchPlan& plan, cudaStream_t stream) {
-    auto kern = gb::search_kernel<Dist, R>;
-    auto slow = gb::search_kernel<Dist, 0>;
-    static std::atomic<bool> attr_set[64];  // function attributes are per device
-    const int dslot = h->device & 63;
-    if (!attr_set[dslot].load()) {
+// next longer fast list for the retry pass (0 = none: go straight to the slow pass)
+constexpr int retry_rows(int R) { return R == 3 ? 7 : (R == 7 ? 15 : (R == 15 ? 31 : 0)); }
+
+template <class Kern>
+int set_smem_attr(Kern kern, Handle* h, std::atomic<bool>* done) {
+    if (!done->load()) {
         GB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
-        GB_CUDA(cudaFuncSetAttribute(slow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
-        attr_set[dslot].store(true);
+        done->store(true);
     }
+    return GRANNE_B200_OK;
+}
+
+template <class Dist, int R>
+int launch_kernels(Handle* h, Workspace* w, gb::SearchArgs a, const LaunchPlan& plan, cudaStream_t stream,
+                   const gb::DeviceIndex& dv) {
+    constexpr int RR = retry_rows(R);
+    auto kern = gb::search_kernel<Dist, R>;
+    auto retry = gb::search_kernel<Dist, (RR > 0 ? RR : 1)>;
+    auto slow = gb::search_kernel<Dist, 0>;
+    static std::atomic<bool> attr_set[64][3];  // function attributes are per device
+    const int dslot = h->device & 63;
+    int rc;
+    if ((rc = set_smem_attr(kern, h, &attr_set[dslot][0]))) return rc;
+    if (RR > 0 && (rc = set_smem_attr(retry, h, &attr_set[dslot][1]))) return rc;
+    if ((rc = set_smem_attr(slow, h, &attr_set[dslot][2]))) return rc;
     // fast pass
     static std::mutex occ_mu;
     static std::map<size_t, int> occ_cache;
@@ -436,50 +484,90 @@ int launch_kernels(Handle* h, Workspace* w, gb::SearchArgs a, const LaunchPlan& 
         }
         a.vis_global = w->d_vis;
     }
-    kern<<<grid, 32, plan.smem, stream>>>(h->dev, a);
+    const bool have_retry = R > 0 && RR > 0;
+    a.pass = 0;
+    a.slow_pass = 0;
+    a.final_pass = 0;
+    a.gate_in = nullptr;
+    a.gate_out = w->d_counters + 3;
+    kern<<<grid, 32, plan.smem, stream>>>(dv, a);
     h->launches++;
     GB_CUDA(cudaGetLastError());
-    // slow pass: re-runs only the queries the fast pass flagged (exits immediately if none)
+    if (have_retry) {
+        // retry pass: only the queries the fast pass flagged (exits at once if none) on a full-size grid of its own,
+        // with the next longer list and 8x larger visited tables — so a batch of heavy queries (e.g. the reference's
+        // uniform test distribution before the table scale has adapted) never funnels through the 4-CTA slow pass
+        gb::SearchArgs r = a;
+        r.pass = 1;
+        r.work_counter = w->d_counters + 1;
+        r.gate_in = w->d_counters + 3;
+        r.gate_out = w->d_counters + 4;
+        r.vis_slots = plan.vis_slots * 8u;
+        r.vis_slots_upper = plan.vis_upper;
+        const unsigned rgrid = (unsigned)std::min<unsigned long long>(a.nq, (unsigned long long)h->num_sms * 4);
+        const size_t need = (size_t)h->num_sms * 4 * r.vis_slots;
+        if (need > w->vis_retry_cap) {
+            GB_CUDA(cudaStreamSynchronize(stream));
+            cudaFree(w->d_vis_retry);
+            w->d_vis_retry = nullptr;
+            w->vis_retry_cap = 0;
+            GB_CUDA(cudaMalloc(&w->d_vis_retry, need * sizeof(uint32_t)));
+            w->vis_retry_cap = need;
+        }
+        r.vis_global = w->d_vis_retry;
+        const size_t rsmem = plan.base_smem + gb::fast_list_bytes(RR > 0 ? RR : 1);
+        retry<<<rgrid, 32, rsmem, stream>>>(dv, r);
+        h->launches++;
+        GB_CUDA(cudaGetLastError());
+    }
+    // slow pass: re-runs only the queries that are still flagged (exits immediately if none)
     gb::SearchArgs s = a;
+    s.pass = 2;
     s.slow_pass = 1;
-    s.work_counter = a.work_counter + 1;
-    slow<<<h->slow_ctas, 32, plan.base_smem, stream>>>(h->dev, s);
+    s.final_pass = 1;
+    s.work_counter = w->d_counters + 2;
+    s.gate_in = w->d_counters + (have_retry ? 4 : 3);
+    s.gate_out = nullptr;
+    slow<<<h->slow_ctas, 32, plan.base_smem, stream>>>(dv, s);
     h->launches++;
     GB_CUDA(cudaGetLastError());
     return GRANNE_B200_OK;
 }
 
 template <class Dist>
-int launch_search(Handle* h, Workspace* w, const gb::SearchArgs& a, const LaunchPlan& plan, cudaStream_t stream) {
+int launch_search(Handle* h, Workspace* w, const gb::SearchArgs& a, const LaunchPlan& plan, cudaStream_t stream,
+                  const gb::DeviceIndex& dv) {
     switch (plan.rows) {
-        case 3: return launch_kernels<Dist, 3>(h, w, a, plan, stream);
-        case 7: return launch_kernels<Dist, 7>(h, w, a, plan, stream);
-        case 15: return launch_kernels<Dist, 15>(h, w, a, plan, stream);
-        case 31: return launch_kernels<Dist, 31>(h, w, a, plan, stream);
-        default: return launch_kernels<Dist, 0>(h, w, a, plan, stream);
+        case 3: return launch_kernels<Dist, 3>(h, w, a, plan, stream, dv);
+        case 7: return launch_kernels<Dist, 7>(h, w, a, plan, stream, dv);
+        case 15: return launch_kernels<Dist, 15>(h, w, a, plan, stream, dv);
+        case 31: return launch_kernels<Dist, 31>(h, w, a, plan, stream, dv);
+        default: return launch_kernels<Dist, 0>(h, w, a, plan, stream, dv);
     }
 }
 
-int dispatch_search(Handle* h, Workspace* w, const gb::SearchArgs& a, const LaunchPlan& plan, cudaStream_t stream) {
-    const gb::DeviceIndex& d = h->dev;
+// `d`: the staged index the kernels see — the handle's own, or a private view of it (compute_order searches single
+// layers without touching the shared handle)
+int dispatch_search(Handle* h, Workspace* w, const gb::SearchArgs& a, const LaunchPlan& plan, cudaStream_t stream,
+                    const gb::DeviceIndex& d) {
     switch (d.kind) {
         case gb::kAngularI8:
-            return launch_search<gb::DistI8>(h, w, a, plan, stream);
+            return launch_search<gb::DistI8>(h, w, a, plan, stream, d);
         case gb::kSumEmbeddings:
-            return launch_search<gb::DistSum>(h, w, a, plan, stream);
+            return launch_search<gb::DistSum>(h, w, a, plan, stream, d);
         default:
             break;
     }
-    if (d.vec_group == 1 && d.full > 4) return launch_search<gb::DistF32Generic>(h, w, a, plan, stream);
+    if (d.vec_group == 1 && d.full > 4) return launch_search<gb::DistF32Generic>(h, w, a, plan, stream, d);
     switch (d.full) {
-        case 0: return launch_search<gb::DistF32<0>>(h, w, a, plan, stream);
-        case 1: return launch_search<gb::DistF32<1>>(h, w, a, plan, stream);
-        case 2: return launch_search<gb::DistF32<2>>(h, w, a, plan, stream);
-        case 3: return launch_search<gb::DistF32<3>>(h, w, a, plan, stream);
-        case 4: return launch_search<gb::DistF32<4>>(h, w, a, plan, stream);
-        case 6: return launch_search<gb::DistF32<6>>(h, w, a, plan, stream);
-        case 8: return launch_search<gb::DistF32<8>>(h, w, a, plan, stream);
-        default: return launch_search<gb::DistF32Generic>(h, w, a, plan, stream);
+        case 0: return launch_search<gb::DistF32<0>>(h, w, a, plan, stream, d);
+        case 1: return launch_search<gb::DistF32<1>>(h, w, a, plan, stream, d);
+        case 2: return launch_search<gb::DistF32<2>>(h, w, a, plan, stream, d);
+        case 3: return launch_search<gb::DistF32<3>>(h, w, a, plan, stream, d);
+        case 4: return launch_search<gb::DistF32<4>>(h, w, a, plan, stream, d);
+        case 6: return launch_search<gb::DistF32<6>>(h, w, a, plan, stream, d);
+        case 8: return launch_search<gb::DistF32<8>>(h, w, a, plan, stream, d);
+        default: return launch_search<gb::DistF32Generic>(h, w, a, plan, stream, d);
     }
 }
 
@@ -495,8 +583,12 @@ int ws_acquire(Handle* h, Workspace** out) {
     }
     std::unique_ptr<Workspace> w(new Workspace());
     GB_CUDA(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
-    GB_CUDA(cudaMalloc(&w->d_counters, 4 * sizeof(unsigned int)));
-    GB_CUDA(cudaMalloc(&w->d_error, 4 * sizeof(int)));
+    GB_CUDA(cudaMalloc(&w->d_counters, 64));
+    w->d_error = reinterpret_cast<int*>(w->d_counters + 8);
+    GB_CUDA(cudaMalloc(&w->d_retried, 8));
+    GB_CUDA(cudaMemset(w->d_retried, 0, 8));
+    GB_CUDA(cudaMallocHost(&w->h_retried, 8));
+    *w->h_retried = 0;
     GB_CUDA(cudaMalloc(&w->d_slow_list, (size_t)h->slow_ctas * h->slow_list_cap * 8));
     w->slow_vis_cap = (size_t)h->slow_ctas * h->slow_vis_slots;
     GB_CUDA(cudaMalloc(&w->d_slow_vis, w->slow_vis_cap * 4));
@@ -510,13 +602,13 @@ void ws_release(Handle* h, Workspace* w) {
 void ws_destroy(Workspace* w) {
     if (!w) return;
     cudaFree(w->d_queries);
-    cudaFree(w->d_ids);
-    cudaFree(w->d_dists);
-    cudaFree(w->d_counts);
+    cudaFree(w->d_ids);  // ids | dists | counts are one block
     cudaFree(w->d_stats);
     cudaFree(w->d_status);
-    cudaFree(w->d_counters);
-    cudaFree(w->d_error);
+    cudaFree(w->d_counters);  // d_error lives inside this block
+    cudaFree(w->d_retried);
+    if (w->h_retried) cudaFreeHost(w->h_retried);
+    cudaFree(w->d_vis_retry);
     cudaFree(w->d_slow_list);
     cudaFree(w->d_slow_vis);
     cudaFree(w->d_vis);
@@ -533,19 +625,17 @@ int ws_reserve(Workspace* w, size_t query_bytes, size_t nq, size_t k) {
         w->queries_cap = query_bytes;
     }
     if (nq * k > w->out_cap_q * w->out_cap_k || nq > w->out_cap_q) {
-        cudaFree(w->d_ids);
-        cudaFree(w->d_dists);
-        cudaFree(w->d_counts);
+        cudaFree(w->d_ids);  // one block: ids | dists | counts, so that one copy brings a whole result back
         cudaFree(w->d_stats);
         w->d_ids = nullptr, w->d_dists = nullptr, w->d_counts = nullptr, w->d_stats = nullptr;
         w->out_cap_q = w->out_cap_k = 0;
-        GB_CUDA(cudaMalloc(&w->d_ids, std::max<size_t>(nq * k, 1) * 4));
-        GB_CUDA(cudaMalloc(&w->d_dists, std::max<size_t>(nq * k, 1) * 4));
-        GB_CUDA(cudaMalloc(&w->d_counts, std::max<size_t>(nq, 1) * 4));
+        GB_CUDA(cudaMalloc(&w->d_ids, (2 * std::max<size_t>(nq * k, 1) + std::max<size_t>(nq, 1)) * 4));
         GB_CUDA(cudaMalloc(&w->d_stats, std::max<size_t>(nq, 1) * 4 * 8));
         w->out_cap_q = nq;
         w->out_cap_k = k;
     }
+    w->d_dists = reinterpret_cast<float*>(w->d_ids + nq * k);  // packed for THIS call's nq x k
+    w->d_counts = w->d_ids + 2 * nq * k;
     const size_t pinned = query_bytes + nq * k * 8 + nq * 4 + nq * 32 + 128;
     if (pinned > w->pinned_cap) {
         if (w->h_pinned) cudaFreeHost(w->h_pinned);
@@ -584,7 +674,8 @@ int validate_search(const Handle* h, const void* q, size_t nq, int fmt, uint32_t
 // Enqueues one batch on `stream` with device pointers.  Needs a workspace for status words / slow path.
 int enqueue_search(Handle* h, Workspace* w, const void* d_queries, size_t nq, int fmt, uint32_t max_search,
                    uint32_t k, uint32_t* d_ids, float* d_dists, uint32_t* d_counts, unsigned long long* d_stats,
-                   cudaStream_t stream, bool reset_error, const granne_b200_peer_gather* pg = nullptr) {
+                   cudaStream_t stream, bool reset_error, const granne_b200_peer_gather* pg = nullptr,
+                   const gb::DeviceIndex* view = nullptr) {
     const LaunchPlan plan = make_plan(h, max_search);
     if (plan.smem == 0 || max_search + 64 > h->slow_list_cap)
         return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "max_search exceeds the supported maximum (about 27000)");
@@ -599,9 +690,26 @@ int enqueue_search(Handle* h, Workspace* w, const void* d_queries, size_t nq, in
         GB_CUDA(cudaMalloc(&w->d_slow_vis, (size_t)h->slow_ctas * h->slow_vis_slots * 4));
         w->slow_vis_cap = (size_t)h->slow_ctas * h->slow_vis_slots;
     }
-    GB_CUDA(cudaMemsetAsync(w->d_counters, 0, 4 * sizeof(unsigned int), stream));
-    if (reset_error) GB_CUDA(cudaMemsetAsync(w->d_error, 0, 4 * sizeof(int), stream));
-    GB_CUDA(cudaMemsetAsync(w->d_status, 0xFF, nq * sizeof(int), stream));
+    // Adapt the visited-table scale to the data: more than 1% of the recent queries needed the retry pass -> double
+    // it (read from the pinned mirror of the device counter, i.e. without synchronising; it lags by a call or two).
+    w->total_queries += nq;
+    {
+        const unsigned long long retried = *reinterpret_cast<volatile unsigned long long*>(w->h_retried);
+        const unsigned long long dq = w->total_queries - w->seen_total, dr = retried - w->seen_retried;
+        if (dq >= 2048) {
+            if (dr * 100 > dq) {
+                uint32_t cur = h->vis_scale.load();
+                // most of the window overflowed: the data simply visits far more nodes -> straight to the maximum
+                const uint32_t next = dr * 2 > dq ? 8u : std::min<uint32_t>(8u, cur * 2);
+                if (cur < next) h->vis_scale.compare_exchange_strong(cur, next);
+            }
+            w->seen_total = w->total_queries;
+            w->seen_retried = retried;
+        }
+    }
+    // one memset per call: the work counters / gates of the three passes (and the error word of a host-API call);
+    // the per-query status words need no reset: the fast pass writes every one of them
+    GB_CUDA(cudaMemsetAsync(w->d_counters, 0, reset_error ? 64 : 32, stream));
     gb::SearchArgs a{};
     a.queries = d_queries;
     a.query_format = fmt;
@@ -617,20 +725,20 @@ int enqueue_search(Handle* h, Workspace* w, const void* d_queries, size_t nq, in
     a.out_stats = d_stats;
     a.query_status = w->d_status;
     a.work_counter = w->d_counters;
-    a.overflow_seen = w->d_counters + 2;
+    a.retried = w->d_retried;
     a.error_flag = w->d_error;
     a.slow_list = w->d_slow_list;
     a.slow_visited = w->d_slow_vis;
     a.slow_list_cap = h->slow_list_cap;
     a.slow_vis_slots = h->slow_vis_slots;
-    a.slow_pass = 0;
+    a.pass = a.slow_pass = a.final_pass = 0;
     a.pg = gb::PeerGather{};
     if (pg) {
         a.pg.n_peers = pg->n_peers;
         a.pg.my_rank = pg->my_rank;
         a.pg.row_offset = pg->row_offset;
         a.pg.seq = pg->seq;
-        a.pg.done_counter = w->d_counters + 3;
+        a.pg.done_counter = w->d_counters + 5;
         for (uint32_t p = 0; p < pg->n_peers; ++p) {
             a.pg.ids[p] = static_cast<uint32_t*>(pg->ids[p]);
             a.pg.dists[p] = static_cast<float*>(pg->dists[p]);
@@ -641,7 +749,10 @@ int enqueue_search(Handle* h, Workspace* w, const void* d_queries, size_t nq, in
     a.stg_row_bytes = plan.stg_row_bytes;
     a.tile_rows = plan.tile_rows;
     a.vis_global = nullptr;
-    return dispatch_search(h, w, a, plan, stream);
+    rc = dispatch_search(h, w, a, plan, stream, view ? *view : h->dev);
+    if (rc) return rc;
+    GB_CUDA(cudaMemcpyAsync(w->h_retried, w->d_retried, 8, cudaMemcpyDeviceToHost, stream));
+    return GRANNE_B200_OK;
 }
 
 int error_from_bits(int bits) {
@@ -879,7 +990,7 @@ int builder_build_partial(Builder* b, uint64_t num_elements) {
         return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "Cannot index fewer elements than already in index.");
     if (num_elements > d.num_elements)
         return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "Cannot index more elements than exist.");
-    GB_CUDA(cudaSetDevice(h->device));
+    GB_DEVICE(h->device);
     int rc;
     if (d.num_layers > 0 && (rc = builder_index_last_layer(b, num_elements))) return rc;
     while (h->index_len < num_elements) {
@@ -954,7 +1065,7 @@ int granne_b200_open_files(const char* index_path, int element_kind, const char*
 
 void granne_b200_close(granne_b200_index* h) {
     if (!h) return;
-    cudaSetDevice(h->device);
+    DeviceGuard guard(h->device);
     cudaDeviceSynchronize();
     for (auto& w : h->pool) ws_destroy(w.get());
     h->pool.clear();
@@ -981,7 +1092,7 @@ int granne_b200_get_neighbors(const granne_b200_index* h, uint64_t idx, uint64_t
     if (!h || !out_n) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "null argument");
     if (layer >= (uint64_t)h->dev.num_layers || idx >= h->dev.layer_len[layer])
         return fail(GRANNE_B200_ERR_OUT_OF_RANGE, "node or layer out of range");
-    GB_CUDA(cudaSetDevice(h->device));
+    GB_DEVICE(h->device);
     const uint32_t w = h->dev.layer_width[layer];
     std::vector<uint32_t> row(w);
     GB_CUDA(cudaMemcpy(row.data(), h->dev.layer_rows[layer] + idx * w, w * 4, cudaMemcpyDeviceToHost));
@@ -996,7 +1107,7 @@ int granne_b200_get_element(const granne_b200_index* hc, uint64_t idx, void* out
     granne_b200_index* h = const_cast<granne_b200_index*>(hc);
     if (!h || !out) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "null argument");
     if (idx >= h->dev.num_elements) return fail(GRANNE_B200_ERR_OUT_OF_RANGE, "element index out of range");
-    GB_CUDA(cudaSetDevice(h->device));
+    GB_DEVICE(h->device);
     const size_t bytes = h->dev.kind == gb::kAngularI8 ? h->dev.dim : (size_t)h->dev.dim * 4;
     void* d = nullptr;
     GB_CUDA(cudaMalloc(&d, bytes));
@@ -1023,7 +1134,7 @@ static int search_device_impl(granne_b200_index* h, const void* d_queries, size_
                 return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "peer gather: null peer pointer");
     }
     if (nq == 0) return GRANNE_B200_OK;
-    GB_CUDA(cudaSetDevice(h->device));
+    GB_DEVICE(h->device);
     cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
     // One workspace per caller stream: calls on the same stream are serialised by the stream itself, so the status
     // words / slow-path buffers can be reused; the error word stays sticky until granne_b200_stream_status().
@@ -1034,10 +1145,23 @@ static int search_device_impl(granne_b200_index* h, const void* d_queries, size_
         if (it != h->stream_ws.end()) w = it->second.get();
     }
     if (!w) {
-        if ((rc = ws_acquire(h, &w))) return rc;
-        GB_CUDA(cudaMemset(w->d_error, 0, 4 * sizeof(int)));
-        std::lock_guard<std::mutex> g(h->pool_mu);
-        h->stream_ws[stream] = std::unique_ptr<Workspace>(w);
+        Workspace* fresh = nullptr;
+        if ((rc = ws_acquire(h, &fresh))) return rc;
+        cudaError_t e = cudaMemset(fresh->d_error, 0, 4 * sizeof(int));
+        bool lost_race = false;
+        {
+            std::lock_guard<std::mutex> g(h->pool_mu);
+            auto it = h->stream_ws.find(stream);  // two threads may meet here on the first use of a stream
+            if (it != h->stream_ws.end()) {
+                w = it->second.get();
+                lost_race = true;
+            } else {
+                h->stream_ws[stream] = std::unique_ptr<Workspace>(fresh);
+                w = fresh;
+            }
+        }
+        if (lost_race) ws_release(h, fresh);  // back to the pool, nothing is leaked
+        GB_CUDA(e);
     }
     return enqueue_search(h, w, d_queries, nq, query_format, max_search, num_neighbors, d_out_ids, d_out_dists,
                           d_out_counts, reinterpret_cast<unsigned long long*>(d_out_stats), stream, false, pg);
@@ -1062,7 +1186,7 @@ int granne_b200_search_batch_device_gather(granne_b200_index* h, const void* d_q
 
 int granne_b200_stream_status(granne_b200_index* h) {
     if (!h) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "index handle is null");
-    GB_CUDA(cudaSetDevice(h->device));
+    GB_DEVICE(h->device);
     GB_CUDA(cudaDeviceSynchronize());
     int bits = h->sticky_error.exchange(0);
     std::lock_guard<std::mutex> g(h->pool_mu);
@@ -1081,7 +1205,7 @@ int granne_b200_search_batch(granne_b200_index* h, const void* queries, size_t n
     int rc = validate_search(h, queries, nq, query_format, max_search, num_neighbors, out_ids, out_dists);
     if (rc) return rc;
     if (nq == 0) return GRANNE_B200_OK;
-    GB_CUDA(cudaSetDevice(h->device));
+    GB_DEVICE(h->device);
     const size_t k = num_neighbors;
     const bool i8q = h->dev.kind == gb::kAngularI8 && query_format == GRANNE_B200_QUERY_ELEMENT;
     const size_t qbytes = nq * h->dev.dim * (i8q ? 1 : 4);
@@ -1108,11 +1232,8 @@ int granne_b200_search_batch(granne_b200_index* h, const void* queries, size_t n
     rc = enqueue_search(h, w, w->d_queries, nq, query_format, max_search, num_neighbors, w->d_ids, w->d_dists,
                         w->d_counts, out_stats ? w->d_stats : nullptr, w->stream, true);
     if (rc) return rc;
-    if (k) {
-        GB_CUDA(cudaMemcpyAsync(hids, w->d_ids, nq * k * 4, cudaMemcpyDeviceToHost, w->stream));
-        GB_CUDA(cudaMemcpyAsync(hd, w->d_dists, nq * k * 4, cudaMemcpyDeviceToHost, w->stream));
-    }
-    GB_CUDA(cudaMemcpyAsync(hc, w->d_counts, nq * 4, cudaMemcpyDeviceToHost, w->stream));
+    // one packed copy: ids | dists | counts (device and pinned layouts match), then the 16-byte error word
+    GB_CUDA(cudaMemcpyAsync(hids, w->d_ids, (2 * nq * k + nq) * 4, cudaMemcpyDeviceToHost, w->stream));
     GB_CUDA(cudaMemcpyAsync(herr, w->d_error, 4 * sizeof(int), cudaMemcpyDeviceToHost, w->stream));
     if (out_stats) GB_CUDA(cudaMemcpyAsync(hstats, w->d_stats, nq * 32, cudaMemcpyDeviceToHost, w->stream));
     GB_CUDA(cudaStreamSynchronize(w->stream));
@@ -1195,7 +1316,7 @@ static int builder_new_impl(const granne_b200_build_config* cfg, int element_kin
         rc = check_device(device, &h->num_sms, &h->smem_optin);
         if (rc) return rc;
         h->device = device;
-        GB_CUDA(cudaSetDevice(device));
+        GB_DEVICE(device);
         if (dev_rows)
             rc = stage_device_elements(h, element_kind, dev_rows, n_dev, dim_dev);
         else
@@ -1249,7 +1370,7 @@ int granne_b200_builder_append(granne_b200_builder* b, const void* elements_byte
         if (dv.num == 0) return GRANNE_B200_OK;
         const uint64_t old_n = d.num_vectors, new_n = old_n + dv.num;
         if (new_n >= 0xFFFFFFFFull) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "too many elements");  // :420
-        GB_CUDA(cudaSetDevice(h->device));
+        GB_DEVICE(h->device);
         GB_CUDA(cudaStreamSynchronize(b->ws->stream));
         const size_t row_bytes = (size_t)d.row_stride * esz;
         uint8_t* dst = nullptr;
@@ -1321,7 +1442,7 @@ int granne_b200_builder_get_neighbors(const granne_b200_builder* b, uint64_t idx
 int granne_b200_write_index(const granne_b200_index* h, void* out, size_t cap, size_t* out_len) {
     if (!h || !out_len) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "null argument");
     try {
-        GB_CUDA(cudaSetDevice(h->device));
+        GB_DEVICE(h->device);
         std::vector<std::vector<uint32_t>> host(h->dev.num_layers);
         std::vector<gb::LayerView> views;
         for (int l = 0; l < h->dev.num_layers; ++l) {
@@ -1373,7 +1494,7 @@ int granne_b200_builder_get_index(granne_b200_builder* b, granne_b200_index** ou
 
 void granne_b200_builder_free(granne_b200_builder* b) {
     if (!b) return;
-    cudaSetDevice(b->h->device);
+    DeviceGuard guard(b->h->device);
     cudaDeviceSynchronize();
     cudaFree(b->d_ids);
     cudaFree(b->d_cand_ids);
@@ -1404,7 +1525,7 @@ int granne_b200_elements_from_raw(int element_kind, const float* raw, uint64_t n
     size_t optin = 0;
     int rc = check_device(device, &sms, &optin);
     if (rc) return rc;
-    GB_CUDA(cudaSetDevice(device));
+    GB_DEVICE(device);
     uint8_t* o = static_cast<uint8_t*>(out);
     for (int b8 = 0; b8 < 8; ++b8) o[b8] = (uint8_t)((uint64_t)dim >> (8 * b8));
     const uint64_t slab = std::max<uint64_t>(1, (256ull << 20) / ((size_t)dim * 4));
@@ -1447,7 +1568,7 @@ int granne_b200_elements_from_raw_device(int element_kind, const float* d_raw, u
     size_t optin = 0;
     int rc = check_device(device, &sms, &optin);
     if (rc) return rc;
-    GB_CUDA(cudaSetDevice(device));
+    GB_DEVICE(device);
     gb::make_elements_kernel<<<(unsigned)std::min<uint64_t>(n, (uint64_t)sms * 32), 32, (size_t)dim * 4,
                                static_cast<cudaStream_t>(cuda_stream)>>>(d_raw, n, dim, element_kind, d_out);
     GB_CUDA(cudaGetLastError());
@@ -1546,7 +1667,7 @@ int granne_b200_compute_order(granne_b200_index* h, uint64_t* order_out, uint64_
     const int nl = h->dev.num_layers;
     if (nl == 0) return GRANNE_B200_OK;
     try {
-        GB_CUDA(cudaSetDevice(h->device));
+        GB_DEVICE(h->device);
         std::vector<uint64_t> layer_lens(nl);
         for (int l = 0; l < nl; ++l) layer_lens[l] = h->dev.layer_len[l];
         const size_t trail_layers = std::min<size_t>(gb::kTrailLayers, (size_t)nl - 1);
@@ -1557,37 +1678,38 @@ int granne_b200_compute_order(granne_b200_index* h, uint64_t* order_out, uint64_
         const size_t batch = (size_t)std::min<uint64_t>(std::max<uint64_t>(n, 1), 1u << 20);
         uint32_t *d_q = nullptr, *d_ids = nullptr, *d_cnt = nullptr;
         float* d_d = nullptr;
-        const gb::DeviceIndex saved = h->dev;
-        struct Cleanup {  // reorder is `&mut self` in the reference: no concurrent searches while the view is swapped
+        // the trail searches run over a PRIVATE single-layer view of the staged index: the shared handle is never
+        // modified, so concurrent searches on it stay correct
+        gb::DeviceIndex view = h->dev;
+        struct Cleanup {
             Handle* h;
             Workspace* w;
-            const gb::DeviceIndex* saved;
             uint32_t **q, **ids, **cnt;
             float** d;
             ~Cleanup() {
-                h->dev = *saved;
                 cudaFree(*q);
                 cudaFree(*ids);
                 cudaFree(*cnt);
                 cudaFree(*d);
                 ws_release(h, w);
             }
-        } cleanup{h, w, &saved, &d_q, &d_ids, &d_cnt, &d_d};
+        } cleanup{h, w, &d_q, &d_ids, &d_cnt, &d_d};
         GB_CUDA(cudaMalloc(&d_q, batch * 4));
         GB_CUDA(cudaMalloc(&d_ids, batch * 4));
         GB_CUDA(cudaMalloc(&d_cnt, batch * 4));
         GB_CUDA(cudaMalloc(&d_d, batch * 4));
         for (size_t j = 0; j < trail_layers; ++j) {
             eps[j].resize(n - layer_lens[j]);
-            h->dev.num_layers = 1;
-            h->dev.layer_rows[0] = saved.layer_rows[j];
-            h->dev.layer_width[0] = saved.layer_width[j];
-            h->dev.layer_len[0] = saved.layer_len[j];
+            view.num_layers = 1;
+            view.layer_rows[0] = h->dev.layer_rows[j];
+            view.layer_width[0] = h->dev.layer_width[j];
+            view.layer_len[0] = h->dev.layer_len[j];
             for (uint64_t base = layer_lens[j]; base < n; base += batch) {
                 const uint64_t bsz = std::min<uint64_t>(batch, n - base);
                 gb::iota_kernel<<<(unsigned)((bsz + 255) / 256), 256, 0, w->stream>>>(d_q, (uint32_t)bsz, (uint32_t)base, 1);
                 h->launches++;
-                rc = enqueue_search(h, w, d_q, bsz, gb::kQueryById, 1, 1, d_ids, d_d, d_cnt, nullptr, w->stream, true);
+                rc = enqueue_search(h, w, d_q, bsz, gb::kQueryById, 1, 1, d_ids, d_d, d_cnt, nullptr, w->stream, true,
+                                    nullptr, &view);
                 if (rc) return rc;
                 GB_CUDA(cudaMemcpyAsync(eps[j].data() + (base - layer_lens[j]), d_ids, bsz * 4, cudaMemcpyDeviceToHost,
                                         w->stream));
@@ -1597,7 +1719,6 @@ int granne_b200_compute_order(granne_b200_index* h, uint64_t* order_out, uint64_
                 if ((rc = error_from_bits(herr[0]))) return rc;
             }
         }
-        h->dev = saved;
         gb::order_from_trails(layer_lens, eps, order_out);
         return GRANNE_B200_OK;
     } catch (const std::exception& e) {
@@ -1705,7 +1826,7 @@ int granne_b200_merge_topk_device(int device, const uint32_t* d_part_ids, const 
         return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "null argument");
     if (num_parts == 0 || num_parts > 64) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "num_parts must be 1..64");
     if (nq == 0 || k == 0) return GRANNE_B200_OK;
-    GB_CUDA(cudaSetDevice(device));
+    GB_DEVICE(device);
     cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
     unsigned long long* d_base = nullptr;
     GB_CUDA(cudaMallocAsync(&d_base, num_parts * 8, stream));

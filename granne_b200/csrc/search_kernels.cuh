@@ -119,15 +119,22 @@ struct SearchArgs {
     uint32_t* out_counts;
     unsigned long long* out_stats;  // nq x 4 or null
     int* query_status;              // nq ints (0 = done ok)
-    unsigned int* work_counter;     // persistent scheduling
-    unsigned int* overflow_seen;    // set by the fast pass when any query needs the slow pass
+    unsigned int* work_counter;     // persistent scheduling (one counter per pass)
+    unsigned int* gate_in;          // passes after the first: run only if *gate_in != 0 (somebody flagged a query)
+    unsigned int* gate_out;         // set when this pass flags a query for the next pass
+    unsigned long long* retried;    // cumulative count of queries that needed more than the first pass (or null)
     int* error_flag;                // sticky device error word (OR of status bits that are final)
     // slow path only: global workspaces (one per slow CTA)
     unsigned long long* slow_list;
     uint32_t* slow_visited;
     uint32_t slow_list_cap;
     uint32_t slow_vis_slots;
-    int slow_pass;  // 0: fast kernel, 1: slow kernel (processes only flagged queries)
+    // Pass ladder: 0 = fast pass over every query; 1 = retry (same kernel shape, longer list, larger visited tables)
+    // over the queries the fast pass flagged; 2 = slow pass (global-memory workspaces) over what is still flagged.
+    // The last pass of a call reports exhaustion as an error and signals the peers of a fused gather.
+    int pass;
+    int slow_pass;   // this pass uses the global slow workspaces (list + visited set)
+    int final_pass;  // nothing comes after this pass
     PeerGather pg;
 };
 
@@ -440,60 +447,124 @@ struct DistF32Generic {
 };
 
 // ANGULAR_INT i8: exact i32 r, dx via dp4a (src/math.rs:59-89), then 1 - r/(sqrt(dx)*sqrt(dy)) in IEEE f32
-// (src/elements/angular_int.rs:47-59).  Rows and the query are zero-padded to row_stride bytes (multiple of 16).
-// Candidate rows are bulk-copied into the staging tile like the f32 rows; lane w then handles 32-bit word w of a row
-// and the exact integer sums are reduced with REDUX (__reduce_add_sync) — integer addition is order independent.
+// (src/elements/angular_int.rs:47-59).  Rows and the query are zero-padded to row_stride bytes (a multiple of 32: a
+// row starts on a sector boundary and touches ceil(dim/32) sectors).
+// Sub-warp groups: a row is C = row_stride/16 chunks of 16 bytes; L = next power of two >= C lanes work on one row
+// (lane handles chunk lane % L), so one pass of the warp handles 32/L candidate rows at once: every lane copies ITS
+// chunk with one cp.async (its own 16-byte slot, no cross-lane hazard), multiplies it with its 16 query bytes held in
+// registers (8 dp4a), and the exact integer sums are reduced inside the group with log2(L) xor-shuffles — integer
+// addition is order independent.  A 100-byte row costs a quarter of a pass instead of a full-warp pass + 2 REDUX.
 struct DistI8 {
     static constexpr bool kStaged = true;
-    static constexpr bool kMbar = true;
-    __device__ __forceinline__ void load_query(const DeviceIndex&, const WarpCtx&) {}
-    template <class Hook>
-    __device__ __forceinline__ float dists(const DeviceIndex& ix, WarpCtx& c, uint32_t my_id, int k, Hook&& after_wait) {
-        const float d = dists(ix, c, my_id, k);
-        after_wait();
+    static constexpr bool kMbar = false;
+    int4 qv;       // the 16 query bytes of this lane's chunk
+    uint32_t lg;   // log2(L)
+    uint32_t C;    // chunks per row (0: rows wider than 512 bytes, generic path)
+
+    __device__ __forceinline__ void load_query(const DeviceIndex& ix, const WarpCtx& c) {
+        const uint32_t chunks = ix.row_stride / 16u;
+        C = chunks <= 32u ? chunks : 0u;
+        uint32_t L = 1;
+        lg = 0;
+        while (L < chunks && L < 32u) {
+            L <<= 1;
+            ++lg;
+        }
+        const uint32_t chunk = (uint32_t)c.lane & (L - 1u);
+        qv = make_int4(0, 0, 0, 0);
+        if (C && chunk < C) qv = reinterpret_cast<const int4*>(c.qs)[chunk];
+    }
+
+    __device__ __forceinline__ float finish(const WarpCtx& c, int my_r, int my_dx, bool live) const {
+        float d = 0.0f;
+        if (live) {
+            const float rf = (float)my_r, dxf = (float)my_dx, dyf = (float)c.q_norm_i8;
+            float qq = __fdiv_rn(rf, __fmul_rn(__fsqrt_rn(dxf), __fsqrt_rn(dyf)));
+            if (qq != qq) qq = 0.0f;  // NotNan::new(..).unwrap_or_else(|_| 0.0)
+            const float dd = __fsub_rn(1.0f, qq);
+            d = (0.0f <= dd) ? dd : 0.0f;
+        }
         return d;
     }
+
     __device__ __forceinline__ float dists(const DeviceIndex& ix, WarpCtx& c, uint32_t my_id, int k) {
         const uint32_t stride = ix.row_stride;
-        const int words = stride / 4;
-        const int* qw = reinterpret_cast<const int*>(c.qs);
+        const int lane = c.lane;
         int my_r = 0, my_dx = 0;
-        const int rb = (int)c.stg_rows;
-        for (int j0 = 0; j0 < k; j0 += rb) {
-            const int nb = (k - j0) < rb ? (k - j0) : rb;
-            const uint32_t id = __shfl_sync(kFullMask, my_id, (j0 + c.lane) & 31);
-            __syncwarp();  // everyone is done reading the previous batch
-            if (c.lane == 0) mbar_arrive_expect_tx(c.bar, (uint32_t)nb * stride);
-            if (c.lane < nb)
-                bulk_copy_g2s(smem_u32(c.stg) + c.lane * stride,
-                              static_cast<const char*>(ix.vectors) + (size_t)id * stride, stride, c.bar, c.pol_stream);
-            mbar_wait(c.bar, c.phase);
-            c.phase ^= 1u;
-            for (int b = 0; b < nb; ++b) {
-                const int* row = reinterpret_cast<const int*>(c.stg + (size_t)b * stride);
+        if (C == 0) {
+            // very wide rows: one candidate at a time, lanes stride over the 32-bit words
+            const int words = stride / 4;
+            const int* qw = reinterpret_cast<const int*>(c.qs);
+            for (int j = 0; j < k; ++j) {
+                const uint32_t id = __shfl_sync(kFullMask, my_id, j);
+                const int* row = reinterpret_cast<const int*>(static_cast<const char*>(ix.vectors) + (size_t)id * stride);
                 int r = 0, dx = 0;
-                for (int w = c.lane; w < words; w += 32) {
-                    const int a = row[w];
+                for (int w = lane; w < words; w += 32) {
+                    const int a = ldg_row_i32(row + w);
                     r = __dp4a(a, qw[w], r);
                     dx = __dp4a(a, a, dx);
                 }
                 r = __reduce_add_sync(kFullMask, r);
                 dx = __reduce_add_sync(kFullMask, dx);
-                if (c.lane == j0 + b) {
+                if (lane == j) {
                     my_r = r;
                     my_dx = dx;
                 }
             }
+            const float d = finish(c, my_r, my_dx, lane < k);
+            __syncwarp();
+            return d;
         }
-        float d = 0.0f;
-        if (c.lane < k) {
-            const float rf = (float)my_r, dxf = (float)my_dx, dyf = (float)c.q_norm_i8;
-            float qv = __fdiv_rn(rf, __fmul_rn(__fsqrt_rn(dxf), __fsqrt_rn(dyf)));
-            if (qv != qv) qv = 0.0f;  // NotNan::new(..).unwrap_or_else(|_| 0.0)
-            const float dd = __fsub_rn(1.0f, qv);
-            d = (0.0f <= dd) ? dd : 0.0f;
+        const uint32_t L = 1u << lg;
+        const int rp = 32 >> lg;                          // candidate rows per pass
+        const int grp = lane >> lg;                       // my row within a pass
+        const uint32_t chunk = (uint32_t)lane & (L - 1u);
+        const bool has_chunk = chunk < C;
+        const int ppb = (int)c.stg_rows;                  // 512-byte pass slots in the staging tile
+        const char* src0 = static_cast<const char*>(ix.vectors) + chunk * 16u;
+        const uint32_t dst0 = smem_u32(c.stg) + lane * 16u;
+        const int4* mine = reinterpret_cast<const int4*>(c.stg) + lane;
+        for (int j0 = 0; j0 < k; j0 += rp * ppb) {
+            const int left = k - j0;
+            const int np = (left + rp - 1) / rp < ppb ? (left + rp - 1) / rp : ppb;
+            for (int p = 0; p < np; ++p) {
+                const int cand = j0 + p * rp + grp;
+                const uint32_t id = __shfl_sync(kFullMask, my_id, cand & 31);
+                if (has_chunk && cand < k) cp_async_lane<16>(dst0 + p * 512u, src0 + (size_t)id * stride);
+            }
+            cp_async_wait_all();
+            for (int p = 0; p < np; ++p) {
+                const int base = j0 + p * rp;
+                int4 a = make_int4(0, 0, 0, 0);
+                if (has_chunk && base + grp < k) a = mine[p * 32];
+                int r = __dp4a(a.x, qv.x, 0);
+                r = __dp4a(a.y, qv.y, r);
+                r = __dp4a(a.z, qv.z, r);
+                r = __dp4a(a.w, qv.w, r);
+                int dx = __dp4a(a.x, a.x, 0);
+                dx = __dp4a(a.y, a.y, dx);
+                dx = __dp4a(a.z, a.z, dx);
+                dx = __dp4a(a.w, a.w, dx);
+                for (uint32_t o = L >> 1; o > 0; o >>= 1) {
+                    r += __shfl_xor_sync(kFullMask, r, o);
+                    dx += __shfl_xor_sync(kFullMask, dx, o);
+                }
+                // every lane of group g now holds the sums of candidate base + g: hand them to lane base + g
+                const int src = ((lane - base) << lg) & 31;
+                const int tr = __shfl_sync(kFullMask, r, src);
+                const int tdx = __shfl_sync(kFullMask, dx, src);
+                if (lane >= base && lane < base + rp) {
+                    my_r = tr;
+                    my_dx = tdx;
+                }
+            }
         }
-        __syncwarp();
+        return finish(c, my_r, my_dx, lane < k);
+    }
+    template <class Hook>
+    __device__ __forceinline__ float dists(const DeviceIndex& ix, WarpCtx& c, uint32_t my_id, int k, Hook&& after_wait) {
+        const float d = dists(ix, c, my_id, k);
+        after_wait();
         return d;
     }
 };
@@ -1445,8 +1516,8 @@ __global__ void __launch_bounds__(32, R > 0 ? GB_MIN_BLOCKS : 1) search_kernel(c
         }
     }
     Dist dist;
-    if (a.slow_pass && *reinterpret_cast<volatile unsigned int*>(a.overflow_seen) == 0u) {  // nothing flagged
-        signal_peers(a, c.lane);
+    if (a.pass && *reinterpret_cast<volatile unsigned int*>(a.gate_in) == 0u) {  // nothing flagged
+        if (a.final_pass) signal_peers(a, c.lane);
         return;
     }
 
@@ -1455,7 +1526,8 @@ __global__ void __launch_bounds__(32, R > 0 ? GB_MIN_BLOCKS : 1) search_kernel(c
         if (c.lane == 0) qi0 = atomicAdd(a.work_counter, 1u);
         const unsigned long long qi = __shfl_sync(kFullMask, qi0, 0);
         if (qi >= a.nq) break;
-        if (a.slow_pass && a.query_status[qi] != kStatusOverflow) continue;  // only flagged queries
+        if (a.pass && a.query_status[qi] != kStatusOverflow) continue;  // only flagged queries
+        if (a.pass == 1 && a.retried && c.lane == 0) atomicAdd(a.retried, 1ull);
 
         c.status = 0;
         c.n_dist = c.n_expand = c.n_nbr = 0;
@@ -1542,13 +1614,13 @@ __global__ void __launch_bounds__(32, R > 0 ? GB_MIN_BLOCKS : 1) search_kernel(c
         if (c.status & kStatusOverflow) {
             // leave the outputs to the slow path (or report capacity exhaustion if this IS the slow path)
             if (c.lane == 0) {
-                a.query_status[qi] = a.slow_pass ? (kStatusOverflow | 4) : kStatusOverflow;
-                if (a.slow_pass)
+                a.query_status[qi] = a.final_pass ? (kStatusOverflow | 4) : kStatusOverflow;
+                if (a.final_pass)
                     atomicOr(a.error_flag, kStatusOverflow);
                 else
-                    atomicExch(a.overflow_seen, 1u);
+                    atomicExch(a.gate_out, 1u);
             }
-            if (!a.slow_pass) continue;
+            if (!a.final_pass) continue;
             found = 0;
         }
         if (c.status & kStatusNotFinite) {
@@ -1562,12 +1634,12 @@ __global__ void __launch_bounds__(32, R > 0 ? GB_MIN_BLOCKS : 1) search_kernel(c
                 a.out_stats[qi * 4 + 0] = c.n_dist;
                 a.out_stats[qi * 4 + 1] = c.n_expand;
                 a.out_stats[qi * 4 + 2] = c.n_nbr;
-                a.out_stats[qi * 4 + 3] = a.slow_pass ? 1ull : 0ull;
+                a.out_stats[qi * 4 + 3] = (unsigned long long)a.pass;
             }
             if (!(c.status & kStatusOverflow)) a.query_status[qi] = 0;
         }
     }
-    if (a.slow_pass) signal_peers(a, c.lane);
+    if (a.final_pass) signal_peers(a, c.lane);
 }
 
 // ------------------------------------------------------------------------------------------------------------------

@@ -62,8 +62,8 @@ extern "C" {
 #define GRANNE_B200_STAT_N_DIST 0
 #define GRANNE_B200_STAT_N_EXPAND 1
 #define GRANNE_B200_STAT_N_NEIGHBORS_READ 2 /* sum of the degrees of the expanded nodes */
-#define GRANNE_B200_STAT_FLAGS 3            /* bit0: query took the exact slow path (workspace overflow);
-                                               other bits reserved (0) */
+#define GRANNE_B200_STAT_FLAGS 3            /* which pass answered the query: 0 = fast pass, 1 = retry pass (longer
+                                               list, larger visited table), 2 = exact slow pass (global workspaces) */
 #define GRANNE_B200_STATS_PER_QUERY 4
 
 typedef struct granne_b200_index granne_b200_index; /* opaque: owns all device + host memory */

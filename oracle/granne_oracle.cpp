@@ -1305,20 +1305,40 @@ void* orc_index_to_fixed(void* p) {
     auto* src = (Index*)p;
     auto* ix = new Index();
     ix->use_fixed = true;
-    size_t w = 1;
-    std::vector<u32> tmp;
-    for (size_t l = 0; l < src->num_layers(); ++l)
-        for (size_t i = 0; i < src->layer_len(l); ++i) {
-            src->get_neighbors(l, i, tmp);
-            w = std::max(w, tmp.size());
+    // decode every list once per pass, node ranges spread over the host threads (a 100M-node layer takes seconds)
+    const unsigned hw = std::max(1u, std::min(64u, std::thread::hardware_concurrency()));
+    auto ranges = [&](size_t n, const std::function<void(size_t, size_t, unsigned)>& fn) {
+        const unsigned t = (unsigned)std::max<size_t>(1, std::min<size_t>(hw, n / 4096));
+        if (t == 1) {
+            fn(0, n, 0);
+            return;
         }
+        std::vector<std::thread> ts;
+        const size_t per = (n + t - 1) / t;
+        for (unsigned w = 0; w < t; ++w)
+            if (w * per < n) ts.emplace_back(fn, w * per, std::min(n, (w + 1) * per), w);
+        for (auto& th : ts) th.join();
+    };
+    std::vector<size_t> wmax(hw, 1);
+    for (size_t l = 0; l < src->num_layers(); ++l)
+        ranges(src->layer_len(l), [&](size_t b, size_t e, unsigned w) {
+            std::vector<u32> tmp;
+            for (size_t i = b; i < e; ++i) {
+                src->get_neighbors(l, i, tmp);
+                wmax[w] = std::max(wmax[w], tmp.size());
+            }
+        });
+    const size_t w = *std::max_element(wmax.begin(), wmax.end());
     ix->width = w;
     for (size_t l = 0; l < src->num_layers(); ++l) {
         std::vector<u32> rows(src->layer_len(l) * w, UNUSED);
-        for (size_t i = 0; i < src->layer_len(l); ++i) {
-            src->get_neighbors(l, i, tmp);
-            std::copy(tmp.begin(), tmp.end(), rows.begin() + i * w);
-        }
+        ranges(src->layer_len(l), [&](size_t b, size_t e, unsigned) {
+            std::vector<u32> tmp;
+            for (size_t i = b; i < e; ++i) {
+                src->get_neighbors(l, i, tmp);
+                std::copy(tmp.begin(), tmp.end(), rows.begin() + i * w);
+            }
+        });
         ix->fixed.push_back(std::move(rows));
     }
     return ix;

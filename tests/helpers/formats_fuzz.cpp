@@ -90,6 +90,20 @@ int main(int argc, char** argv) {
             gb::parse_dense(eb.data(), eb.size(), kind == 0 ? 4 : 1, &v, &err);
         }
     }
+    // hostile width prefixes: width * scalar_bytes wraps in 64 bits (2^62 * 4 == 0 used to divide by zero, 2^62 + 1
+    // wrapped to 4 and was accepted with dim ~ 2^62) — all must be rejected with a status, never crash
+    for (uint64_t w : {1ull << 62, (1ull << 62) + 1, 1ull << 63, ~0ull, (1ull << 61) + 3, 1ull << 41}) {
+        Bytes img(8 + 64, 0);
+        for (int b = 0; b < 8; ++b) img[b] = (uint8_t)(w >> (8 * b));
+        for (size_t sb : {size_t(4), size_t(1)}) {
+            gb::DenseView v;
+            std::string err;
+            if (gb::parse_dense(img.data(), img.size(), sb, &v, &err)) {
+                std::printf("hostile width %llu accepted\n", (unsigned long long)w);
+                return 3;
+            }
+        }
+    }
     std::printf("parsed %ld rejected %ld\n", parsed, rejected);
     return 0;
 }

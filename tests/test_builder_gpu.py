@@ -133,7 +133,7 @@ def test_builder_queries_that_overflow_the_fast_path():
     index = b.get_index()
     ids, d, c, st = index.search_batch(random_vectors(2000, 64, seed=12), 40, 10, with_stats=True)
     assert (c == 10).all()
-    assert int((st[:, 3] & 1).sum()) > 0  # the slow pass really is exercised with these parameters
+    assert int((st[:, 3] != 0).sum()) > 0  # passes beyond the fast one really are exercised with these parameters
     rows = np.frombuffer(eb, dtype=np.float32, offset=8).reshape(30_000, 64)
     assert _self_recall(index, rows[:3000], 40) > 0.9
     index.close()

@@ -36,7 +36,7 @@ def test_result_properties_at_full_size(big):
 
     index, eb, image, q = big
     ids, d, c, st = index.search_batch(q, EF, K, with_stats=True)
-    assert (c == K).all() and ((st[:, 3] & 1) == 0).all()
+    assert (c == K).all() and (st[:, 3] == 0).all()
     # ascending by (distance, id): the order of into_sorted_vec (src/index/mod.rs:1036); ids are distinct and in range
     assert (np.diff(d, axis=1) >= 0).all()
     ties = np.diff(d, axis=1) == 0

@@ -58,7 +58,7 @@ def test_c1_parity_raw_queries(c1):
     q = random_vectors(1000, 32, seed=4321)
     ref, got = run_both(g, p, q, 50, 10)
     assert_parity(ref, got, "C1")
-    assert ((got[3][:, 3] & 1) == 0).all()  # nobody needed the slow path
+    assert (got[3][:, 3] == 0).all()  # nobody needed more than the fast pass
 
 
 @pytest.mark.parametrize("ef,k", [(1, 1), (1, 5), (2, 2), (10, 10), (50, 1), (50, 50), (50, 80), (200, 10), (333, 100)])
@@ -202,7 +202,7 @@ def test_all_identical_vectors_take_the_exact_slow_path(oracle):
     q = random_vectors(8, dim, seed=6)
     ref, got = run_both(g, p, q, 20, 10)
     assert_parity(ref, got, "plateau")
-    assert ((got[3][:, 3] & 1) == 1).all()    # flagged: served by the slow path
+    assert (got[3][:, 3] == 2).all()    # flagged twice (fast pass, retry pass): served by the slow pass
     assert (ref[3][:, 1] > 20).all()           # equal-distance frontier entries are expanded beyond max_search
     # the same index with a roomy max_search stays on the fast path
     ref, got = run_both(g, p, q, 300, 10)
