@@ -780,17 +780,51 @@ def main():
             self.stop = True
             self.go.wait()
 
-    hp = HostPool()
-    hp.run(max(a.warmup, 2 * nthreads), 0)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize(dev)
-    t0 = time.perf_counter()
-    hp.run(a.steps, 3)
-    torch.cuda.synchronize(dev)
-    e2e_s = time.perf_counter() - t0
-    e2e_thread_ms = max(hp.issue_s) * 1e3
-    hp.close()
+    if partitioned:
+        # range-partitioned: the end-to-end path of one step is host queries -> every rank's GPU -> local search ->
+        # all-gather -> merge -> merged (global id, distance) tiles back on the host.  Collectives are issued from
+        # one thread per rank (NCCL), round-robin on the same streams, with pinned host buffers on both ends.
+        nthreads = 1
+        d2h = a.nq * a.k * 12
+        q_pin = torch.from_numpy(q_host).pin_memory()
+        res_pin = [(torch.empty((a.nq, a.k), dtype=torch.int64).pin_memory(),
+                    torch.empty((a.nq, a.k), dtype=torch.float32).pin_memory()) for _ in streams]
+
+        def host_step(s):
+            slot = s % len(streams)
+            with torch.cuda.stream(streams[slot]):
+                b = s % pool
+                qin[slot].copy_(q_pin[b * a.nq:(b + 1) * a.nq], non_blocking=True)
+                step_body(slot)
+                res_pin[slot][0].copy_(merged[slot][0], non_blocking=True)
+                res_pin[slot][1].copy_(merged[slot][1], non_blocking=True)
+
+        for s in range(max(a.warmup, len(streams))):
+            host_step(s)
+        sync_all()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for s in range(a.steps):
+            host_step(a.warmup + s)
+        sync_all()
+        e2e_s = time.perf_counter() - t0
+        e2e_thread_ms = e2e_s * 1e3
+        e2e_api = "granne_b200.distributed.PartitionedGranne path (search_batch_device + all_gather + merge_topk)"
+    else:
+        hp = HostPool()
+        hp.run(max(a.warmup, 2 * nthreads), 0)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        hp.run(a.steps, 3)
+        torch.cuda.synchronize(dev)
+        e2e_s = time.perf_counter() - t0
+        e2e_thread_ms = max(hp.issue_s) * 1e3
+        hp.close()
+        e2e_api = "granne_b200.Granne.search_batch (granne_b200_search_batch)"
     if world > 1:
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -827,7 +861,7 @@ def main():
         "recall_at_10": recall,
         "e2e": {"value": e2e_qps, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "host_threads": nthreads, "host_issue_ms_per_step": e2e_thread_ms / max(1, a.steps / nthreads),
-                "cpu_affinity": cpus, "api": "granne_b200.Granne.search_batch (granne_b200_search_batch)"},
+                "cpu_affinity": cpus, "api": e2e_api},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
