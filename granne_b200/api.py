@@ -84,6 +84,12 @@ def load_library():
         "granne_b200_builder_free": (None, [vp]),
         "granne_b200_elements_from_raw": (i32, [i32, vp, u64, u32, i32, vp, sz, C.POINTER(sz)]),
         "granne_b200_launch_count": (u64, [vp]),
+        "granne_b200_multi_open": (i32, [i32, vp, sz, i32, vp, vp, vp, vp, sz, vp, sz, C.POINTER(vp)]),
+        "granne_b200_multi_close": (None, [vp]),
+        "granne_b200_multi_len": (u64, [vp]),
+        "granne_b200_multi_num_parts": (sz, [vp]),
+        "granne_b200_multi_shard_base": (u64, [vp, sz]),
+        "granne_b200_multi_search_batch": (i32, [vp, vp, sz, i32, u32, u32, vp, vp, vp]),
         "granne_b200_device_bytes": (u64, [vp]),
     }
     for name, (res, args) in sig.items():
@@ -421,6 +427,86 @@ class Granne:
 
     def device_bytes(self):
         return int(load_library().granne_b200_device_bytes(self._h))
+
+
+MODE_REPLICATED, MODE_RANGE_PARTITIONED = 0, 1
+
+
+class MultiGranne:
+    """Several GPUs of THIS process behind one handle (granne_b200_multi_*): no torch, no NCCL.
+
+    MultiGranne.replicated(index_bytes, element_type, elements_bytes, devices)       one index on every device,
+                                                                                     query batches are sliced
+    MultiGranne.partitioned([(index_bytes, elements_bytes), ...], element_type, devices)
+                                                                                     one independent index per shard
+    search_batch returns GLOBAL uint64 ids (0xFFFF_FFFF_FFFF_FFFF padded), float32 distances, counts."""
+
+    def __init__(self, mode, shards, element_type, devices, embeddings_bytes=None):
+        L = load_library()
+        kind = _kind(element_type)
+        n = len(shards)
+        self._keep = [(np.frombuffer(i, dtype=np.uint8), np.frombuffer(e, dtype=np.uint8)) for i, e in shards]
+        ip = (C.c_void_p * n)(*[a.ctypes.data for a, _ in self._keep])
+        il = (C.c_size_t * n)(*[a.size for a, _ in self._keep])
+        ep = (C.c_void_p * n)(*[b.ctypes.data for _, b in self._keep])
+        el = (C.c_size_t * n)(*[b.size for _, b in self._keep])
+        dv = (C.c_int * len(devices))(*[int(d) for d in devices])
+        mb = np.frombuffer(embeddings_bytes, dtype=np.uint8) if embeddings_bytes is not None else None
+        h = C.c_void_p()
+        _check(L.granne_b200_multi_open(mode, dv, len(devices), kind, ip, il, ep, el, n,
+                                        _ptr(mb) if mb is not None else None, mb.size if mb is not None else 0,
+                                        C.byref(h)))
+        self._h = h
+        self._keep = None
+        self.kind = kind
+        self.mode = mode
+
+    @classmethod
+    def replicated(cls, index_bytes, element_type, elements_bytes, devices, embeddings_bytes=None):
+        return cls(MODE_REPLICATED, [(index_bytes, elements_bytes)], element_type, devices, embeddings_bytes)
+
+    @classmethod
+    def partitioned(cls, shards, element_type, devices, embeddings_bytes=None):
+        return cls(MODE_RANGE_PARTITIONED, shards, element_type, devices, embeddings_bytes)
+
+    def __len__(self):
+        return int(load_library().granne_b200_multi_len(self._h))
+
+    def num_parts(self):
+        return int(load_library().granne_b200_multi_num_parts(self._h))
+
+    def shard_base(self, s):
+        return int(load_library().granne_b200_multi_shard_base(self._h, s))
+
+    def search_batch(self, queries, max_search=DEFAULT_MAX_SEARCH, num_elements=DEFAULT_NUM_ELEMENTS,
+                     already_element=False):
+        q = np.asarray(queries)
+        fmt = QUERY_ELEMENT if already_element else QUERY_RAW_F32
+        if q.dtype == np.int8:
+            fmt = QUERY_ELEMENT
+            q = np.ascontiguousarray(q)
+        else:
+            q = np.ascontiguousarray(q, dtype=np.float32)
+        if q.ndim != 2:
+            raise ValueError("queries must have shape (nq, dim)")
+        nq, k = q.shape[0], int(num_elements)
+        ids = np.empty((nq, k), dtype=np.uint64)
+        dists = np.empty((nq, k), dtype=np.float32)
+        counts = np.empty(nq, dtype=np.uint32)
+        _check(load_library().granne_b200_multi_search_batch(self._h, _ptr(q), nq, fmt, int(max_search), k, _ptr(ids),
+                                                             _ptr(dists), _ptr(counts)))
+        return ids, dists, counts
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load_library().granne_b200_multi_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class PeerGather(C.Structure):

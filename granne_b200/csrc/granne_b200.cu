@@ -13,7 +13,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <limits>
 #include <map>
+#include <thread>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -1837,6 +1839,184 @@ int granne_b200_merge_topk_device(int device, const uint32_t* d_part_ids, const 
     GB_CUDA(cudaGetLastError());
     GB_CUDA(cudaFreeAsync(d_base, stream));
     return GRANNE_B200_OK;
+}
+
+// ---- several GPUs behind one handle ------------------------------------------------------------------------------------
+}  // extern "C"
+
+struct granne_b200_multi {
+    int mode = GRANNE_B200_MODE_REPLICATED;
+    std::vector<granne_b200_index*> parts;  // one single-device handle per device (replicated) or per shard
+    std::vector<uint64_t> base;              // global id of each part's element 0
+    uint64_t total_len = 0;
+    uint32_t dim = 0;
+    int kind = 0;
+};
+
+namespace {
+
+// runs fn(i) for i in [0, n) on n threads (one per device: every call blocks on its own stream) and returns the
+// first non-zero status together with its message
+template <class F>
+int for_each_part(size_t n, F&& fn) {
+    std::vector<int> rc(n, 0);
+    std::vector<std::string> msg(n);
+    std::vector<std::thread> th;
+    for (size_t i = 1; i < n; ++i)
+        th.emplace_back([&, i] {
+            rc[i] = fn(i);
+            if (rc[i]) msg[i] = g_last_error;  // thread_local: carry it to the caller's thread
+        });
+    rc[0] = fn(0);
+    if (rc[0]) msg[0] = g_last_error;
+    for (auto& t : th) t.join();
+    for (size_t i = 0; i < n; ++i)
+        if (rc[i]) return fail(rc[i], msg[i]);
+    return GRANNE_B200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int granne_b200_multi_open(int mode, const int* devices, size_t num_devices, int element_kind,
+                           const void* const* index_bytes, const size_t* index_len,
+                           const void* const* elements_bytes, const size_t* elements_len, size_t num_shards,
+                           const void* embeddings_bytes, size_t embeddings_len, granne_b200_multi** out) {
+    if (!out) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "out handle pointer is null");
+    *out = nullptr;
+    if (mode != GRANNE_B200_MODE_REPLICATED && mode != GRANNE_B200_MODE_RANGE_PARTITIONED)
+        return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "unknown multi-GPU mode");
+    if (!devices || num_devices == 0 || num_devices > 64)
+        return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "device list must name 1..64 devices");
+    if (!index_bytes || !index_len || !elements_bytes || !elements_len || num_shards == 0)
+        return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "null argument");
+    if (mode == GRANNE_B200_MODE_REPLICATED && num_shards != 1)
+        return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "replicated mode takes exactly one index image");
+    try {
+        std::unique_ptr<granne_b200_multi> m(new granne_b200_multi());
+        m->mode = mode;
+        m->kind = element_kind;
+        const size_t n = mode == GRANNE_B200_MODE_REPLICATED ? num_devices : num_shards;
+        m->parts.assign(n, nullptr);
+        m->base.assign(n, 0);
+        int rc = for_each_part(n, [&](size_t i) {
+            const size_t s = mode == GRANNE_B200_MODE_REPLICATED ? 0 : i;
+            return granne_b200_open(index_bytes[s], index_len[s], element_kind, elements_bytes[s], elements_len[s],
+                                    embeddings_bytes, embeddings_len, devices[i % num_devices], &m->parts[i]);
+        });
+        if (rc) {
+            const std::string keep = g_last_error;
+            for (auto* p : m->parts) granne_b200_close(p);
+            return fail(rc, keep);
+        }
+        m->dim = m->parts[0]->dev.dim;
+        uint64_t acc = 0;
+        for (size_t i = 0; i < n; ++i) {
+            if (m->parts[i]->dev.dim != m->dim) {
+                for (auto* p : m->parts) granne_b200_close(p);
+                return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "shards have different dimensions");
+            }
+            if (mode == GRANNE_B200_MODE_RANGE_PARTITIONED) {
+                m->base[i] = acc;
+                acc += m->parts[i]->dev.num_elements;  // ids continue across shards over the ELEMENT ranges
+            }
+        }
+        m->total_len = 0;
+        if (mode == GRANNE_B200_MODE_REPLICATED)
+            m->total_len = m->parts[0]->index_len;
+        else
+            for (auto* p : m->parts) m->total_len += p->index_len;
+        *out = m.release();
+        return GRANNE_B200_OK;
+    } catch (const std::exception& e) {
+        return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, std::string("exception: ") + e.what());
+    }
+}
+
+void granne_b200_multi_close(granne_b200_multi* m) {
+    if (!m) return;
+    for (auto* p : m->parts) granne_b200_close(p);
+    delete m;
+}
+
+uint64_t granne_b200_multi_len(const granne_b200_multi* m) { return m ? m->total_len : 0; }
+size_t granne_b200_multi_num_parts(const granne_b200_multi* m) { return m ? m->parts.size() : 0; }
+uint64_t granne_b200_multi_shard_base(const granne_b200_multi* m, size_t s) {
+    return (m && s < m->base.size()) ? m->base[s] : 0;
+}
+
+int granne_b200_multi_search_batch(granne_b200_multi* m, const void* queries, size_t nq, int query_format,
+                                   uint32_t max_search, uint32_t num_neighbors, uint64_t* out_ids, float* out_dists,
+                                   uint32_t* out_counts) {
+    if (!m) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "multi handle is null");
+    if (nq == 0) return GRANNE_B200_OK;
+    if (!queries || (num_neighbors && (!out_ids || !out_dists)))
+        return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "null buffer");
+    try {
+        const size_t n = m->parts.size(), k = num_neighbors;
+        const bool i8q = m->kind == GRANNE_B200_ANGULAR_INT && query_format == GRANNE_B200_QUERY_ELEMENT;
+        const size_t qrow = (size_t)m->dim * (i8q ? 1 : 4);
+        const uint8_t* q = static_cast<const uint8_t*>(queries);
+        if (m->mode == GRANNE_B200_MODE_REPLICATED) {
+            // contiguous, balanced query slices (the first nq % n devices take one more)
+            std::vector<uint32_t> ids(nq * k);
+            std::vector<uint32_t> cnt(nq);
+            const size_t per = nq / n, extra = nq % n;
+            int rc = for_each_part(n, [&](size_t i) {
+                const size_t b = i * per + std::min(i, extra), cntq = per + (i < extra ? 1 : 0);
+                if (cntq == 0) return (int)GRANNE_B200_OK;
+                return granne_b200_search_batch(m->parts[i], q + b * qrow, cntq, query_format, max_search, num_neighbors,
+                                                ids.data() + b * k, out_dists + b * k, cnt.data() + b, nullptr);
+            });
+            if (rc) return rc;
+            for (size_t i = 0; i < nq * k; ++i) out_ids[i] = ids[i] == gb::kUnusedId ? ~0ull : (uint64_t)ids[i];
+            if (out_counts) std::memcpy(out_counts, cnt.data(), nq * 4);
+            return GRANNE_B200_OK;
+        }
+        // range-partitioned: every shard searches all queries; k-way merge by (distance, global id) on the host
+        std::vector<uint32_t> ids(n * nq * k);
+        std::vector<float> ds(n * nq * k);
+        int rc = for_each_part(n, [&](size_t i) {
+            return granne_b200_search_batch(m->parts[i], q, nq, query_format, max_search, num_neighbors,
+                                            ids.data() + i * nq * k, ds.data() + i * nq * k, nullptr, nullptr);
+        });
+        if (rc) return rc;
+        std::vector<size_t> cur(n);
+        for (size_t qi = 0; qi < nq; ++qi) {
+            std::fill(cur.begin(), cur.end(), 0);
+            uint32_t found = 0;
+            for (size_t r = 0; r < k; ++r) {
+                int best = -1;
+                float bd = 0.0f;
+                uint64_t bid = 0;
+                for (size_t p = 0; p < n; ++p) {
+                    if (cur[p] >= k) continue;
+                    const size_t o = (p * nq + qi) * k + cur[p];
+                    if (ids[o] == gb::kUnusedId) continue;  // each tile is sorted and padded at the end
+                    const uint64_t gid = m->base[p] + ids[o];
+                    if (best < 0 || ds[o] < bd || (ds[o] == bd && gid < bid)) {
+                        best = (int)p;
+                        bd = ds[o];
+                        bid = gid;
+                    }
+                }
+                if (best < 0) {
+                    out_ids[qi * k + r] = ~0ull;
+                    out_dists[qi * k + r] = std::numeric_limits<float>::infinity();
+                } else {
+                    out_ids[qi * k + r] = bid;
+                    out_dists[qi * k + r] = bd;
+                    cur[best] += 1;
+                    found += 1;
+                }
+            }
+            if (out_counts) out_counts[qi] = found;
+        }
+        return GRANNE_B200_OK;
+    } catch (const std::exception& e) {
+        return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, std::string("exception: ") + e.what());
+    }
 }
 
 }  // extern "C"

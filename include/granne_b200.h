@@ -175,6 +175,38 @@ int granne_b200_merge_topk_device(int device, const uint32_t* d_part_ids, const 
                                   const uint64_t* part_base, size_t num_parts, size_t nq, uint32_t k,
                                   uint64_t* d_out_ids, float* d_out_dists, void* cuda_stream);
 
+/* ---- several GPUs behind one handle (SURVEY.md §8b "Load" row: device list + mode; §8e) ------------------------------
+ * For callers without torch / NCCL (a Rust or C++ host): one process drives all the devices.  Queries are independent
+ * (`search` takes &self, src/index/mod.rs:140-150), so neither mode has a data-path collective.
+ *   GRANNE_B200_MODE_REPLICATED        one index image, staged on every listed device; a query batch is split into
+ *                                      contiguous slices, one per device; results are identical to a single device.
+ *   GRANNE_B200_MODE_RANGE_PARTITIONED num_shards independent (index, elements) pairs — granne's own sharding of the
+ *                                      element set (src/elements/embeddings/parsing.rs:63-100) — shard s staged on
+ *                                      devices[s % num_devices]; every query is searched on every shard and the
+ *                                      per-shard lists are merged by (distance, global id), the order of
+ *                                      into_sorted_vec (src/index/mod.rs:1036); global id = shard_base[s] + local id.
+ * `devices` may name a device more than once (several shards per GPU).  index/elements arrays hold num_shards
+ * entries (1 for REPLICATED); the embeddings table (EMBEDDINGS kind) is shared by all shards. */
+#define GRANNE_B200_MODE_REPLICATED 0
+#define GRANNE_B200_MODE_RANGE_PARTITIONED 1
+typedef struct granne_b200_multi granne_b200_multi;
+int granne_b200_multi_open(int mode, const int* devices, size_t num_devices, int element_kind,
+                           const void* const* index_bytes, const size_t* index_len,
+                           const void* const* elements_bytes, const size_t* elements_len, size_t num_shards,
+                           const void* embeddings_bytes, size_t embeddings_len, granne_b200_multi** out);
+void granne_b200_multi_close(granne_b200_multi* m);
+/* Index::len over all shards (replicated: of the one index). */
+uint64_t granne_b200_multi_len(const granne_b200_multi* m);
+/* number of staged single-device handles (devices for REPLICATED, shards for RANGE_PARTITIONED) */
+size_t granne_b200_multi_num_parts(const granne_b200_multi* m);
+/* global id of shard s's element 0 (0 for REPLICATED) */
+uint64_t granne_b200_multi_shard_base(const granne_b200_multi* m, size_t s);
+/* Granne::search for nq queries (HOST buffers, as granne_b200_search_batch); out_ids are u64 GLOBAL ids padded with
+ * UINT64_MAX, out_dists padded with +inf, out_counts may be NULL.  Thread-safe like the single-device call. */
+int granne_b200_multi_search_batch(granne_b200_multi* m, const void* queries, size_t nq, int query_format,
+                                   uint32_t max_search, uint32_t num_neighbors, uint64_t* out_ids, float* out_dists,
+                                   uint32_t* out_counts);
+
 /* Host-only helpers (no device needed): the loader's view of an index image.
  * granne_b200_inspect_index replaces io::read_layer_sizes + Index::num_layers/layer_len on raw bytes
  * (src/index/io.rs:89-113): writes the number of layers and, for up to `cap` layers, the node count, the maximum
