@@ -360,11 +360,17 @@ struct LaunchPlan {
     bool staged;
 };
 
-bool is_staged_kind(const gb::DeviceIndex& d) {
-    // DistI8, and DistF32<FULL> with FULL > 0 (see dispatch_search)
-    if (d.kind == gb::kAngularI8) return true;
+bool is_templated_f32(const gb::DeviceIndex& d) {
+    // DistF32<FULL> with FULL > 0 (see dispatch_search)
     return d.kind == gb::kAngularF32 && d.full > 0 && !(d.vec_group == 1 && d.full > 4) &&
            (d.full <= 4 || d.full == 6 || d.full == 8);
+}
+bool is_generic_f32_staged(const gb::DeviceIndex& d) {
+    // DistF32Generic stages rows of up to 8 KB (dim < 2080); wider rows load directly
+    return d.kind == gb::kAngularF32 && !is_templated_f32(d) && d.full >= 1 && d.full <= 64;
+}
+bool is_staged_kind(const gb::DeviceIndex& d) {
+    return d.kind == gb::kAngularI8 || is_templated_f32(d) || is_generic_f32_staged(d);
 }
 
 LaunchPlan make_plan(const Handle* h, uint32_t max_search) {
@@ -384,6 +390,7 @@ LaunchPlan make_plan(const Handle* h, uint32_t max_search) {
     const uint32_t qbytes = (d.kind == gb::kAngularI8) ? d.row_stride : ((d.dim + 3u) & ~3u) * 4u;
     p.staged = is_staged_kind(d);
     p.tile_rows = d.kind == gb::kAngularI8 ? 0u : ((p.staged || d.kind == gb::kSumEmbeddings) ? 8u : 32u);
+    const bool generic_staged = is_generic_f32_staged(d);
     size_t base = gb::tile_bytes_for_rows(p.tile_rows) + 16 + ((qbytes + 15u) & ~15u) * (d.kind == gb::kSumEmbeddings ? 2 : 1);
     p.stg_rows = 0;
     p.stg_row_bytes = 0;
@@ -398,6 +405,11 @@ LaunchPlan make_plan(const Handle* h, uint32_t max_search) {
         p.stg_row_bytes = 512;
         p.stg_rows = std::max<uint32_t>(2, (unsigned)GB_STG_BYTES / 512u);
         base = ((base + 127) & ~size_t(127)) + (size_t)p.stg_rows * p.stg_row_bytes;
+    } else if (generic_staged) {
+        const uint32_t row_bytes = d.full * 128u;
+        p.stg_row_bytes = row_bytes;
+        p.stg_rows = std::min<uint32_t>(8u, std::max<uint32_t>(2, (unsigned)(2 * GB_STG_BYTES) / row_bytes));
+        base = ((base + 127) & ~size_t(127)) + (size_t)p.stg_rows * row_bytes;
     } else if (p.staged) {
         const uint32_t row_bytes = d.full * 128u;
         p.stg_row_bytes = row_bytes;

@@ -407,41 +407,86 @@ struct DistF32 {
     }
 };
 
-// ANGULAR f32, any dim (runtime chunk count; natural row layout; query read from shared memory).
+// ANGULAR f32, any dim (runtime chunk count; natural row layout; query read from shared memory): the dims the
+// compile-time engines do not cover (dim/32 in {5, 7, 9, ...}: 160, 224, 300 ...).  Staged like DistF32: lane l copies
+// float l of every 32-chunk with a 4-byte cp.async (one instruction moves 128 contiguous bytes), reads the same bytes
+// back for its accumulator chunk[l], and the ordered 32-lane sums of a batch run through the 8-row tile.  Rows too
+// wide for the staging tile (stg_rows == 0) load directly.
 struct DistF32Generic {
     static constexpr bool kStaged = false;
     static constexpr bool kMbar = false;
     __device__ __forceinline__ void load_query(const DeviceIndex&, const WarpCtx&) {}
-    template <class Hook>
-    __device__ __forceinline__ float dists(const DeviceIndex& ix, WarpCtx& c, uint32_t my_id, int k, Hook&& after_wait) {
-        const float d = dists(ix, c, my_id, k);
-        after_wait();
-        return d;
+
+    static __device__ __forceinline__ float ordered_finish(const DeviceIndex& ix, WarpCtx& c, uint32_t id, int trow) {
+        float r = 0.0f;
+        const float4* t = reinterpret_cast<const float4*>(c.tile + trow * kTileStride);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float4 v = t[i];
+            r = __fadd_rn(r, v.x);
+            r = __fadd_rn(r, v.y);
+            r = __fadd_rn(r, v.z);
+            r = __fadd_rn(r, v.w);
+        }
+        const int full = ix.full;
+        const float* row = static_cast<const float*>(ix.vectors) + (size_t)id * ix.row_stride + full * 32;
+        const float* qt = c.qs + full * 32;
+        for (int t2 = 0; t2 < (int)ix.tail; ++t2) r = __fmaf_rn(__ldg(row + t2), qt[t2], r);
+        return finish_angular(r, &c.status);
     }
+
     __device__ __forceinline__ float dists(const DeviceIndex& ix, WarpCtx& c, uint32_t my_id, int k) {
         const float* base = static_cast<const float*>(ix.vectors);
         const size_t stride = ix.row_stride;
         const int full = ix.full;
-        for (int j = 0; j < k; ++j) {
-            const uint32_t id = __shfl_sync(kFullMask, my_id, j);
-            const float* row = base + (size_t)id * stride + c.lane;
-            float p = 0.0f;
-            for (int ch = 0; ch < full; ++ch) p = __fmaf_rn(ldg_row_f1(row + ch * 32), c.qs[ch * 32 + c.lane], p);
-            c.tile[j * kTileStride + c.lane] = p;
-        }
-        __syncwarp();
         float d = 0.0f;
-        if (c.lane < k) {
-            float r = 0.0f;
-            const float* t = c.tile + c.lane * kTileStride;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) r = __fadd_rn(r, t[i]);
-            const float* row = base + (size_t)my_id * stride + full * 32;
-            const float* qt = c.qs + full * 32;
-            for (int t2 = 0; t2 < (int)ix.tail; ++t2) r = __fmaf_rn(__ldg(row + t2), qt[t2], r);
-            d = finish_angular(r, &c.status);
+        if (c.stg_rows == 0 || full == 0) {
+            // direct loads, one candidate after the other (32-row tile)
+            for (int j = 0; j < k; ++j) {
+                const uint32_t id = __shfl_sync(kFullMask, my_id, j);
+                const float* row = base + (size_t)id * stride + c.lane;
+                float p = 0.0f;
+                for (int ch = 0; ch < full; ++ch) p = __fmaf_rn(ldg_row_f1(row + ch * 32), c.qs[ch * 32 + c.lane], p);
+                c.tile[j * kTileStride + c.lane] = p;
+            }
+            __syncwarp();
+            if (c.lane < k) d = ordered_finish(ix, c, my_id, c.lane);
+            __syncwarp();
+            return d;
         }
-        __syncwarp();
+        const uint32_t row_bytes = (uint32_t)full * 128u;
+        const char* src0 = reinterpret_cast<const char*>(base) + c.lane * 4;
+        const uint32_t dst0 = smem_u32(c.stg) + c.lane * 4u;
+        const float* mine = reinterpret_cast<const float*>(c.stg) + c.lane;
+        const int rb = (int)c.stg_rows;  // <= 8 = tile rows
+        for (int j0 = 0; j0 < k; j0 += rb) {
+            const int nb = (k - j0) < rb ? (k - j0) : rb;
+            for (int b = 0; b < nb; ++b) {
+                const uint32_t idb = __shfl_sync(kFullMask, my_id, j0 + b);
+                const char* src = src0 + (size_t)idb * stride * 4u;
+                for (int ch = 0; ch < full; ++ch) cp_async_lane<4>(dst0 + b * row_bytes + ch * 128, src + ch * 128);
+            }
+            cp_async_wait_all();
+            for (int b = 0; b < nb; ++b) {
+                const float* r = mine + b * full * 32;
+                float p = 0.0f;
+                for (int ch = 0; ch < full; ++ch) p = __fmaf_rn(r[ch * 32], c.qs[ch * 32 + c.lane], p);
+                c.tile[b * kTileStride + c.lane] = p;
+            }
+            __syncwarp();
+            const uint32_t id = __shfl_sync(kFullMask, my_id, (j0 + c.lane) & 31);  // lane t: candidate j0 + t
+            float db = 0.0f;
+            if (c.lane < nb) db = ordered_finish(ix, c, id, c.lane);
+            const float dj = __shfl_sync(kFullMask, db, (c.lane - j0) & 31);
+            if (c.lane >= j0 && c.lane < j0 + nb) d = dj;
+            __syncwarp();
+        }
+        return d;
+    }
+    template <class Hook>
+    __device__ __forceinline__ float dists(const DeviceIndex& ix, WarpCtx& c, uint32_t my_id, int k, Hook&& after_wait) {
+        const float d = dists(ix, c, my_id, k);
+        after_wait();
         return d;
     }
 };
