@@ -1,35 +1,41 @@
-"""Profiling driver for ncu: builds the bench index with the GPU builder and runs a few search batches.
-Usage: python tools/prof_search.py [n] [nq] [iters] [dim]"""
+"""Profiling driver for ncu: the bench workload (same generator, same per-box index cache as bench.py) and a few search
+batches; the last one sits in the NVTX range "prof".
+Usage: python tools/prof_search.py [config=c2] [nq=32768] [iters=3] [elements=0]"""
 import os
 import sys
-
-import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
+import bench  # noqa: E402
 import granne_b200  # noqa: E402
-from bench import clustered  # noqa: E402
 
-n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
-nq = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
+cfg = sys.argv[1] if len(sys.argv) > 1 else "c2"
+nq = int(sys.argv[2]) if len(sys.argv) > 2 else 32768
 iters = int(sys.argv[3]) if len(sys.argv) > 3 else 3
-dim = int(sys.argv[4]) if len(sys.argv) > 4 else 128
-nc = max(8, int(4096 * (n / 1e6) ** 0.5))
-eb = granne_b200.elements_from_raw("angular", clustered(n, dim, 1234, nc))
-b = granne_b200.GranneBuilder("angular", eb, num_neighbors=30, max_search=200)
-b.build()
-p = b.get_index()
-b.close()
-tq = torch.from_numpy(clustered(nq, dim, 4321, nc)).cuda()
+sys.argv = [sys.argv[0], "--config", cfg] + (["--elements", sys.argv[4]] if len(sys.argv) > 4 and int(sys.argv[4]) else [])
+a = bench.parse_args()
+a.nq = nq
+granne_b200.load_library()
+dev = torch.device("cuda", 0)
+torch.cuda.set_device(0)
+tables = bench.device_tables(torch, dev, a, a.n)
+el = bench.make_elements_device(torch, granne_b200, dev, a, a.n, bench.DATA_SEED, tables)
+p, _, prov = bench.build_or_load_index(torch, granne_b200, a, dev, el, bench.DATA_SEED)
+del el
+torch.cuda.empty_cache()
+tq = bench.make_queries_device(torch, dev, a, nq, bench.QUERY_SEED, tables)
+stats = torch.zeros((nq, 4), dtype=torch.int64, device=dev)
 out = None
 for it in range(iters):
     if it == iters - 1:
         torch.cuda.synchronize()
         torch.cuda.nvtx.range_push("prof")
-    out = p.search_batch_device(tq, 200, 10, out=out)
+    out = p.search_batch_device(tq, a.max_search, a.k, out=out, stats=stats if it == 0 else None)
 torch.cuda.synchronize()
 torch.cuda.nvtx.range_pop()
 p.stream_status()
-print("done")
+s = stats.cpu().numpy()
+print("done: config %s n=%d nq=%d index %s; n_expand total %d, n_dist total %d" % (
+    cfg, a.n, nq, prov.get("source"), int(s[:, 1].sum()), int(s[:, 0].sum())))
