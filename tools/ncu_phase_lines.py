@@ -15,8 +15,8 @@ marks = [("pop+spec", find("// ---- pq.pop(): first unexpanded", f0)),
          ("adjacency", find("// ---- neighbours ----", f0)),
          ("visited(call)", find("const bool is_new = vis_bucket_insert", f0)),
          ("compact", find("if (is_new) c.ids[", f0)),
-         ("dist(call)", find("const float d = dist.dists(ix, c, my_id, k);", f0)),
-         ("spec prefetch", find("// The speculative row arrived", f0)),
+         ("dist(call)", find("const float d = dist.dists(ix, c, my_id, k", f0)),
+         ("spec buckets (hook)", find("candidate rows are in flight the speculative adjacency row lands too", f0)),
          ("pass filter", find("// !res.is_full() || distance < res.peek().0   (:1029)", f0)),
          ("merge: park+rank", find("// park the passing keys", f0)),
          ("merge: rank_n", find("// rank among the new keys", f0)),
@@ -27,6 +27,7 @@ marks = [("pop+spec", find("// ---- pq.pop(): first unexpanded", f0)),
 vis0, vis1 = find("__device__ __forceinline__ bool vis_bucket_insert("), find("// search_for_neighbors (src/index/mod.rs:999-1037) on one layer.")
 d0 = find("struct DistF32 {"); d1 = find("// ANGULAR f32, any dim (runtime chunk count")
 issue = find("cp_async_wait_all();", d0); part = find("c.tile[b * kTileStride + c.lane] = partial(", d0); osum = find("uint32_t id = 0;", d0)
+marks.sort(key=lambda m: m[1])
 def phase(ln):
     if vis0 <= ln < vis1: return "visited"
     if d0 <= ln < d1:
