@@ -55,6 +55,8 @@ CONFIGS = {
     "c4": ("angular", 100_000_000, 128, "replicated", "BASELINE.json configs[3]"),
     "c5": ("angular_int", 12_500_000, 96, "partitioned", "BASELINE.json configs[4] family (1B/8 = 125M per shard "
                                                           "scaled to what builds in the time budget)"),
+    "emb": ("embeddings", 1_000_000, 100, "replicated", "not a BASELINE config: granne's third element type, "
+                                                         "SumEmbeddings — elements of 2..9 terms over n/5 embeddings"),
 }
 
 
@@ -69,7 +71,7 @@ def parse_args():
                     help="number of indexed elements (per shard in partitioned mode); 0 = the config's own "
                          "(not --n: torchrun would claim that prefix)")
     ap.add_argument("--dim", type=int, default=0)
-    ap.add_argument("--kind", default="", choices=["", "angular", "angular_int"])
+    ap.add_argument("--kind", default="", choices=["", "angular", "angular_int", "embeddings"])
     ap.add_argument("--mode", default="", choices=["", "replicated", "partitioned"])
     ap.add_argument("--nq", type=int, default=1024, help="queries per step (per GPU in replicated mode)")
     ap.add_argument("--max-search", type=int, default=200)
@@ -167,6 +169,126 @@ def make_queries_device(torch, dev, a, nq_total, seed, tables):
     return out
 
 
+# ---- element containers ------------------------------------------------------------------------------------------------
+class DenseContainer:
+    """angular / angular_int: element rows resident in HBM (a CUDA tensor [n, dim])."""
+
+    def __init__(self, torch, granne_b200, dev, a, n, seed, tables):
+        self.torch, self.gb, self.a, self.n = torch, granne_b200, a, n
+        self.rows = make_elements_device(torch, granne_b200, dev, a, n, seed, tables)
+        self.terms_per_element = 0.0
+
+    def open(self, index_bytes):
+        return self.gb.Granne.from_device_elements(index_bytes, self.a.kind, self.rows)
+
+    def builder(self):
+        return self.gb.GranneBuilder.from_device_elements(self.a.kind, self.rows, num_neighbors=self.a.num_neighbors,
+                                                          max_search=200)
+
+    def ground_truth_block(self, s0, s1):
+        blk = self.rows[s0:s1]
+        return blk if self.a.kind == "angular" else self.torch.nn.functional.normalize(blk.float(), dim=1)
+
+    def to_oracle(self, go):
+        host = self.rows.cpu().numpy()
+        return go.Elements.angular(host, as_is=True) if self.a.kind == "angular" else go.Elements.angular_int(host)
+
+    def free(self):
+        self.rows = None
+        self.torch.cuda.empty_cache()
+
+
+def pack_le(values, nbytes):
+    """little-endian `nbytes`-byte integers, vectorised (odd_byte_int.rs:3-36)"""
+    v = np.asarray(values, dtype=np.uint64)
+    out = np.empty((v.size, nbytes), dtype=np.uint8)
+    for b in range(nbytes):
+        out[:, b] = (v >> np.uint64(8 * b)) & np.uint64(0xFF)
+    return out.reshape(-1)
+
+
+class SumContainer:
+    """embeddings::SumEmbeddings: an embedding table + per-element term lists (file images, as the reference's own
+    constructors take them: SumEmbeddings::from_bytes, src/elements/embeddings/mod.rs:56-61)."""
+
+    def __init__(self, torch, granne_b200, dev, a, n, seed):
+        self.torch, self.gb, self.a, self.n, self.dev = torch, granne_b200, a, n, dev
+        n_emb = max(1000, n // 5)
+        n_centers = max(8, int(4096 * (n_emb / 1e6) ** 0.5))
+        rng = np.random.default_rng(seed)
+        brng = np.random.default_rng(7)
+        basis = brng.standard_normal((16, a.dim)).astype(np.float32)
+        centers = brng.standard_normal((n_centers, 16)).astype(np.float32)
+        which = rng.integers(0, n_centers, size=n_emb)
+        emb = (centers[which] + 0.3 * rng.standard_normal((n_emb, 16)).astype(np.float32)) @ basis
+        self.emb = emb.astype(np.float32)
+        order = np.argsort(which, kind="stable")
+        counts = np.bincount(which, minlength=n_centers)
+        starts = np.concatenate([[0], np.cumsum(counts)[:-1]])
+        self.groups = (order, starts, counts, np.nonzero(counts)[0])
+        lens, terms = self.sample_elements(rng, n)
+        self.offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+        self.terms = terms
+        self.terms_per_element = float(lens.mean())
+        self.elements_image = np.concatenate([np.frombuffer(int(n).to_bytes(8, "little"), dtype=np.uint8),
+                                              pack_le(self.offsets, 5), pack_le(terms, 3)])
+        self.embeddings_image = np.concatenate([np.frombuffer(int(a.dim).to_bytes(8, "little"), dtype=np.uint8),
+                                                self.emb.reshape(-1).view(np.uint8)])
+        self._rows = None
+
+    def sample_elements(self, rng, n):
+        """elements of 2 + i % 8 terms (src/test_helper.rs:39-43) drawn from ONE cluster of embeddings each"""
+        order, starts, counts, nonempty = self.groups
+        c = nonempty[rng.integers(0, nonempty.size, size=n)]
+        lens = 2 + (np.arange(n) % 8)
+        pick = starts[c][:, None] + np.floor(rng.random((n, 9)) * counts[c][:, None]).astype(np.int64)
+        mask = np.arange(9)[None, :] < lens[:, None]
+        return lens, order[pick][mask].astype(np.uint32)
+
+    def raw_vectors(self, lens, terms):
+        """un-normalised sums of the term rows (what a caller of the reference passes as a query vector)"""
+        owner = np.repeat(np.arange(lens.size), lens)
+        out = np.zeros((lens.size, self.a.dim), dtype=np.float32)
+        np.add.at(out, owner, self.emb[terms])
+        return out
+
+    def queries(self, nq_total, seed):
+        lens, terms = self.sample_elements(np.random.default_rng(seed), nq_total)
+        return self.raw_vectors(lens, terms)
+
+    def open(self, index_bytes):
+        return self.gb.Granne.from_bytes(index_bytes, "embeddings", self.elements_image, self.embeddings_image,
+                                         device=self.dev.index)
+
+    def builder(self):
+        return self.gb.GranneBuilder("embeddings", self.elements_image, self.embeddings_image,
+                                     num_neighbors=self.a.num_neighbors, max_search=200, device=self.dev.index)
+
+    def ground_truth_block(self, s0, s1):
+        torch = self.torch
+        if self._rows is None:
+            emb = torch.from_numpy(self.emb).to(self.dev)
+            lens = np.diff(self.offsets.astype(np.int64))
+            owner = torch.from_numpy(np.repeat(np.arange(self.n), lens)).to(self.dev)
+            rows = torch.zeros((self.n, self.a.dim), dtype=torch.float32, device=self.dev)
+            rows.index_add_(0, owner, emb[torch.from_numpy(self.terms.astype(np.int64)).to(self.dev)])
+            self._rows = torch.nn.functional.normalize(rows, dim=1)
+        return self._rows[s0:s1]
+
+    def to_oracle(self, go):
+        return go.Elements.from_bytes("embeddings", self.elements_image.tobytes(), self.embeddings_image.tobytes())
+
+    def free(self):
+        self._rows = None
+        self.torch.cuda.empty_cache()
+
+
+def make_container(torch, granne_b200, dev, a, n, seed, tables):
+    if a.kind == "embeddings":
+        return SumContainer(torch, granne_b200, dev, a, n, seed)
+    return DenseContainer(torch, granne_b200, dev, a, n, seed, tables)
+
+
 # ---- index cache -------------------------------------------------------------------------------------------------------
 def cache_path(a, n, seed):
     if not a.cache:
@@ -203,17 +325,16 @@ def cache_store(path, index_bytes, meta):
         print("bench: index cache not written (%r)" % (e,), file=sys.stderr)
 
 
-def build_or_load_index(torch, granne_b200, a, dev, elements, seed):
+def build_or_load_index(torch, granne_b200, a, dev, container, seed):
     """(index handle, index file image, provenance dict).  The image is what both arms search."""
-    path = cache_path(a, elements.shape[0], seed)
+    path = cache_path(a, container.n, seed)
     data, meta = cache_load(path)
     t0 = time.time()
     if data is not None:
-        index = granne_b200.Granne.from_device_elements(data, a.kind, elements)
+        index = container.open(data)
         return index, data, {"source": "cache", "built_by": meta.get("built_by"), "build_s": meta.get("build_s"),
                              "load_s": time.time() - t0}
-    b = granne_b200.GranneBuilder.from_device_elements(a.kind, elements, num_neighbors=a.num_neighbors,
-                                                       max_search=200)
+    b = container.builder()
     b.build()
     build_s = time.time() - t0
     index = b.get_index()
@@ -228,7 +349,7 @@ def build_or_load_index(torch, granne_b200, a, dev, elements, seed):
 
 
 def workload_config(a, impl, n_used, world, prov=None):
-    et = "f32" if a.kind == "angular" else "i8"
+    et = {"angular": "f32", "angular_int": "i8", "embeddings": "sum-of-embeddings f32"}[a.kind]
     shards = world if a.mode == "partitioned" else 1
     return {"workload": "%s%dx%d angular %s HNSW (M=%d, build max_search=200), search max_search=%d k=%d, "
                         "%d queries/step%s" % ("%d shards x " % shards if shards > 1 or a.mode == "partitioned" else "",
@@ -242,7 +363,7 @@ def workload_config(a, impl, n_used, world, prov=None):
             "index_provenance": dict(prov or {}, shared="both arms search the same granne index file image "
                                                          "(cached per box)"),
             "l2": "inputs larger than L2 (%.0f MB vectors + adjacency; query batches rotate)"
-                  % (n_used * a.dim * (4 if a.kind == "angular" else 1) / 1e6), "streams": a.streams, "impl": impl}
+                  % (n_used * a.dim * (1 if a.kind == "angular_int" else 4) / 1e6), "streams": a.streams, "impl": impl}
 
 
 class ClockSampler:
@@ -356,22 +477,20 @@ def spread_over_all_cores():
 
 
 # ---- CPU side (the oracle: test infrastructure, used here only as the timed CPU baseline / reference arm) -------------
-def oracle_index(a, index_bytes, elements_host):
+def oracle_index(a, index_bytes, container):
     from oracle import granne_oracle as go
 
-    if a.kind == "angular":
-        el = go.Elements.angular(elements_host, as_is=True)
-    else:
-        el = go.Elements.angular_int(elements_host)
+    el = container.to_oracle(go)
     g = go.Granne.from_bytes(np.asarray(index_bytes), el)   # compressed adjacency decoded per expansion (faithful)
     return go, el, g
 
 
-def cpu_baseline(a, index_bytes, elements_host, queries, seconds):
+def cpu_baseline(a, index_bytes, container, queries, seconds):
     """The CPU restatement of the reference (oracle/) on this box's host cores, bounded sample."""
     threads = os.cpu_count() or 1
     placement = spread_over_all_cores()
-    go, el, g = oracle_index(a, index_bytes, elements_host)
+    go, el, g = oracle_index(a, index_bytes, container)
+    container.free()
     gf = g.to_fixed()                                  # pre-decoded adjacency (the stronger CPU variant)
     probe = queries[:max(threads * 2, 64)]
     t = time.time()
@@ -422,14 +541,14 @@ def run_reference(a):
             t_setup = time.time()
             for r in range(world):
                 tables = device_tables(torch, dev, a, n)
-                el_dev = make_elements_device(torch, granne_b200, dev, a, n, DATA_SEED + r, tables)
-                index, data, prov = build_or_load_index(torch, granne_b200, a, dev, el_dev, DATA_SEED + r)
+                cont = make_container(torch, granne_b200, dev, a, n, DATA_SEED + r, tables)
+                index, data, prov = build_or_load_index(torch, granne_b200, a, dev, cont, DATA_SEED + r)
                 index.close()
-                host = el_dev.cpu().numpy()
-                del el_dev, index
-                torch.cuda.empty_cache()
-                go, el, g = oracle_index(a, data, host)
-                del host
+                del index
+                go, el, g = oracle_index(a, data, cont)
+                if r == world - 1 and a.kind == "embeddings":
+                    query_src = cont
+                cont.free()
                 shards.append((el, g, g.to_fixed(), prov))
             break
         except (RuntimeError, MemoryError, granne_b200.GranneError) as e:
@@ -440,7 +559,10 @@ def run_reference(a):
             torch.cuda.empty_cache()
     tables = device_tables(torch, dev, a, n)
     pool = 16
-    queries = make_queries_device(torch, dev, a, max(a.nq * pool, 1 << 15), QUERY_SEED, tables).cpu().numpy()
+    if a.kind == "embeddings":
+        queries = query_src.queries(max(a.nq * pool, 1 << 15), QUERY_SEED)
+    else:
+        queries = make_queries_device(torch, dev, a, max(a.nq * pool, 1 << 15), QUERY_SEED, tables).cpu().numpy()
     setup_s = time.time() - t_setup
 
     from granne_b200.distributed import merge_topk_host
@@ -471,7 +593,7 @@ def run_reference(a):
     prov = shards[0][3]
     line = {"metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if a.kind == "angular" else "i8", "data": "synthetic", "impl": "reference",
+            "dtype": "i8" if a.kind == "angular_int" else "f32", "data": "synthetic", "impl": "reference",
             "config": workload_config(a, "reference", n, a.gpus, prov),
             "cpu_baseline": {"value": qps, "unit": UNIT, "cores": threads,
                              "kind": "port (C++ restatement of the Rust reference; not pinned against a run of the "
@@ -534,12 +656,12 @@ def main():
             seed = DATA_SEED + (rank if partitioned else 0)
             t0 = time.time()
             tables = device_tables(torch, dev, a, n)
-            elements = make_elements_device(torch, granne_b200, dev, a, n, seed, tables)
+            cont = make_container(torch, granne_b200, dev, a, n, seed, tables)
             t_data = time.time() - t0
             t0 = time.time()
             path = cache_path(a, n, seed)
             if partitioned or rank == 0 or (path and os.path.exists(path)):
-                index, index_bytes, prov = build_or_load_index(torch, granne_b200, a, dev, elements, seed)
+                index, index_bytes, prov = build_or_load_index(torch, granne_b200, a, dev, cont, seed)
                 ok = 1
             else:
                 index, index_bytes, prov, ok = None, None, None, 1
@@ -550,7 +672,7 @@ def main():
                     if data is None:  # no shared cache directory: fall back to a broadcast of the image
                         ok = 0
                     else:
-                        index = granne_b200.Granne.from_device_elements(data, a.kind, elements)
+                        index = cont.open(data)
                         index_bytes, prov = data, {"source": "cache", "built_by": meta.get("built_by"),
                                                    "build_s": meta.get("build_s")}
                 flag = torch.tensor([ok], device=dev)
@@ -564,7 +686,7 @@ def main():
                     dist.broadcast(buf, 0)
                     if index is None:
                         index_bytes = buf.cpu().numpy()
-                        index = granne_b200.Granne.from_device_elements(index_bytes, a.kind, elements)
+                        index = cont.open(index_bytes)
                         prov = {"source": "broadcast from rank 0"}
                     del buf
             t_build = time.time() - t0
@@ -574,14 +696,18 @@ def main():
                 raise
             print("bench: setup failed at n=%d (%r); retrying with %d elements" % (n, e, n // 10), file=sys.stderr)
             n //= 10
-            elements = index = None
+            cont = index = None
             torch.cuda.empty_cache()
 
     # ---- queries: a rotating pool of distinct batches per rank --------------------------------------------------------
     pool = 16
     qseed = QUERY_SEED + (0 if partitioned else rank)      # partitioned: every rank searches the same queries
-    q_dev = make_queries_device(torch, dev, a, a.nq * pool, qseed, tables)
-    q_host = q_dev.cpu().numpy()
+    if a.kind == "embeddings":
+        q_host = cont.queries(a.nq * pool, qseed)
+        q_dev = torch.from_numpy(q_host).to(dev)
+    else:
+        q_dev = make_queries_device(torch, dev, a, a.nq * pool, qseed, tables)
+        q_host = q_dev.cpu().numpy()
     streams = [torch.cuda.Stream(device=dev) for _ in range(max(1, a.streams))]
     # per stream: one int32 buffer [2, nq, k] = ids | distance bits (a single all-gather collects both), + counts
     bufs = [torch.empty((2, a.nq, a.k), dtype=torch.int32, device=dev) for _ in streams]
@@ -653,10 +779,13 @@ def main():
     st_np = stats.cpu().numpy()
     n_dist, n_expand, n_nbr = st_np[:, 0].mean(), st_np[:, 1].mean(), st_np[:, 2].mean()
     retried = float((st_np[:, 3] != 0).mean())
-    esz = 4 if a.kind == "angular" else 1
-    bytes_per_query = n_dist * a.dim * esz + n_nbr * 4 + a.dim * esz  # vectors + adjacency + query
+    esz = 1 if a.kind == "angular_int" else 4
+    # vectors + adjacency + query; SumEmbeddings: t term rows + 3-byte ids + two 5-byte offsets per
+    # distance (t = mean terms per element of the container)
+    per_dist = a.dim * esz if a.kind != "embeddings" else cont.terms_per_element * (a.dim * 4 + 3) + 10
+    bytes_per_query = n_dist * per_dist + n_nbr * 4 + a.dim * esz
     nsamp = min(256, a.nq)
-    if a.kind == "angular":
+    if a.kind != "angular_int":
         qn = torch.nn.functional.normalize(q_dev[:nsamp], dim=1)
     else:  # ground truth under the same i8 angular distance: cosine of the quantised vectors
         qq = q_dev[:nsamp]
@@ -664,9 +793,7 @@ def main():
         qn = torch.nn.functional.normalize(qq, dim=1)
     best = None
     for s0 in range(0, n, 1 << 20):  # exact brute force in slabs over the device-resident elements (off the hot path)
-        blk = elements[s0:s0 + (1 << 20)]
-        if a.kind != "angular":
-            blk = torch.nn.functional.normalize(blk.float(), dim=1)
+        blk = cont.ground_truth_block(s0, min(n, s0 + (1 << 20)))
         sc = qn @ blk.T
         v, i = torch.topk(sc, a.k, dim=1)
         i = i + s0
@@ -681,13 +808,10 @@ def main():
     gt = best[1].cpu().numpy()
     got = ids0[:nsamp].cpu().numpy()
     recall = float(np.mean([len(set(gt[i].tolist()) & set(got[i].tolist())) / a.k for i in range(nsamp)]))
-    # the host copy of the elements is only needed by the CPU baseline (rank 0, N = 1)
-    elements_host = None
+    # the container is only needed again by the CPU baseline (rank 0, N = 1), which copies it to the host
     want_cpu = world == 1 and rank == 0 and a.cpu_seconds > 0 and not partitioned
-    if want_cpu:
-        elements_host = elements.cpu().numpy()
-    del elements
-    torch.cuda.empty_cache()
+    if not want_cpu:
+        cont.free()
 
     # ---- device-resident timed region ------------------------------------------------------------------------------------
     for s in range(max(a.warmup, len(streams))):
@@ -851,12 +975,12 @@ def main():
             traffic = None
     cpu = None
     if want_cpu:
-        cpu = cpu_baseline(a, index_bytes, elements_host, q_host, a.cpu_seconds)
-    kern = {"angular": "DistF32<%d>" % (a.dim // 32), "angular_int": "DistI8"}[a.kind]
+        cpu = cpu_baseline(a, index_bytes, cont, q_host, a.cpu_seconds)
+    kern = {"angular": "DistF32<%d>" % (a.dim // 32), "angular_int": "DistI8", "embeddings": "DistSum"}[a.kind]
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32" if a.kind == "angular" else "i8", "data": "synthetic (generated on the GPU)",
+        "dtype": "i8" if a.kind == "angular_int" else "f32", "data": "synthetic (generated on the GPU)",
         "config": workload_config(a, "ours", n, world, prov),
         "recall_at_10": recall,
         "e2e": {"value": e2e_qps, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -587,7 +587,8 @@ class GranneBuilder:
 
     GranneBuilder(element_type, elements_bytes, embeddings_bytes=None, num_neighbors=30, max_search=200,
                   layer_multiplier=15.0, reinsert_elements=True, expected_num_elements=None, device=0)
-    `elements_bytes` is an elements file image (see elements_from_raw / Granne.save_elements)."""
+    `elements_bytes` is an elements file image (see elements_from_raw / Granne.save_elements).  num_neighbors may be
+    anything the file format can hold (1..255: a list's length is one byte); show_progress is accepted and ignored."""
 
     def __init__(self, element_type, elements_bytes, embeddings_bytes=None, num_neighbors=30, max_search=200,
                  layer_multiplier=15.0, reinsert_elements=True, expected_num_elements=None, show_progress=False,
@@ -646,11 +647,25 @@ class GranneBuilder:
         becomes an element (`Vector::from`) and is pushed; it is indexed by the next build().  Rows are buffered and
         handed to the library in one batch."""
         if _kind(self._element_type) == EMBEDDINGS:
-            raise ValueError("append is implemented for the angular and angular_int containers")
+            # SumEmbeddings::push (src/elements/embeddings/mod.rs:97-100): an element is a list of embedding ids
+            # (the reference's WordEmbeddingsBuilder maps a string to ids first, py/src/variants/builder.rs:84-93)
+            if isinstance(element, str):
+                raise ValueError("pass embedding ids (WordDict.get_word_ids(text)) — this builder holds no word list")
+            self._pending.append([int(t) for t in element])
+            return
         self._pending.append(np.asarray(element, dtype=np.float32))
 
     def _flush(self):
         if not self._pending:
+            return
+        if _kind(self._element_type) == EMBEDDINGS:
+            from . import words as W
+
+            fresh, self._pending = self._pending, []
+            image = np.frombuffer(W.write_sum_terms(fresh), dtype=np.uint8)
+            _check(load_library().granne_b200_builder_append(self._h, _ptr(image), image.size))
+            if self._elements_bytes is not None:
+                self._elements_bytes = W.write_sum_terms(W.read_sum_terms(bytes(self._elements_bytes)) + fresh)
             return
         raw = np.stack(self._pending)
         self._pending = []

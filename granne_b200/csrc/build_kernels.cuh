@@ -63,13 +63,25 @@ __device__ __forceinline__ void node_unlock(int* locks, uint32_t i, int lane) {
 
 // per-warp scratch for linking (shared memory)
 struct LinkScratch {
-    uint32_t* cid;   // candidate ids   (capacity >= max(cand_stride, 40))
+    uint32_t* cid;   // candidate ids   (capacity >= max(cand_stride, node_width + 8, 40))
     float* cd;       // candidate dists
-    uint32_t* sid;   // selected ids    (32)
-    float* sd;       // selected dists  (32)
+    uint32_t* sid;   // selected ids    (node slots = node_width rounded up to 32)
+    float* sd;       // selected dists
     uint32_t* oid;   // the element's own selection (kept while neighbours are pruned)
     float* od;
+    uint32_t* tid;   // add_and_limit: the node's current neighbours (+ the extra one) before sorting (node slots + 8)
+    float* td;
 };
+__host__ __device__ constexpr uint32_t link_node_slots(uint32_t node_width) { return (node_width + 31u) & ~31u; }
+// candidate scratch: the search results of one element, or a node's neighbours + 1 (whichever is larger)
+__host__ __device__ constexpr uint32_t link_cand_cap(uint32_t cand_stride, uint32_t node_width) {
+    return cand_stride > node_width + 8 ? (cand_stride > 40 ? cand_stride : 40)
+                                        : (node_width + 8 > 40 ? node_width + 8 : 40);
+}
+// bytes of shared memory the link scratch needs behind the search context
+__host__ __device__ constexpr size_t link_scratch_bytes(uint32_t cand_cap, uint32_t node_width) {
+    return (size_t)cand_cap * 8 + (size_t)link_node_slots(node_width) * 16 + (size_t)(link_node_slots(node_width) + 8) * 8;
+}
 
 // select_neighbors (:849-883) over candidates cid/cd[0..nc) sorted by distance; result in sid/sd, returns count.
 template <class Dist>
@@ -91,10 +103,14 @@ __device__ __forceinline__ int select_neighbors(const DeviceIndex& ix, WarpCtx& 
         bool ok = true;
         if (ns > 0) {
             // add j if it is closer to idx than to every neighbour selected so far: d <= dist(n, element j)
+            // (32 selected neighbours per distance batch: num_neighbors is not limited to a warp's width)
             set_query_from_element(ix, c, dist, j);
-            const uint32_t my = s.sid[lane < ns ? lane : 0];
-            const float dn = dist.dists(ix, c, my, ns);
-            ok = !__any_sync(kFullMask, (lane < ns) && !(d <= dn));
+            for (int b = 0; b < ns && ok; b += 32) {
+                const int nb = (ns - b) < 32 ? (ns - b) : 32;
+                const uint32_t my = s.sid[b + (lane < nb ? lane : 0)];
+                const float dn = dist.dists(ix, c, my, nb);
+                ok = !__any_sync(kFullMask, (lane < nb) && !(d <= dn));
+            }
         }
         if (ok) {
             if (lane == 0) {
@@ -109,40 +125,52 @@ __device__ __forceinline__ int select_neighbors(const DeviceIndex& ix, WarpCtx& 
 }
 
 // add_and_limit_neighbors (:923-959) for node i (lock held or exclusive access); extra = (ej, ed) if has_extra.
+// Rows wider than a warp are handled 32 slots at a time.
 template <class Dist>
 __device__ __forceinline__ void add_and_limit(const DeviceIndex& ix, WarpCtx& c, Dist& dist, LinkScratch& s,
                                               uint32_t* rows, uint32_t stride, uint32_t node_width, uint32_t i,
                                               bool has_extra, uint32_t ej, float ed, int limit) {
     const int lane = c.lane;
     uint32_t* row = rows + (size_t)i * stride;
-    const uint32_t v = ((uint32_t)lane < node_width) ? __ldcg(row + lane) : kUnusedId;
-    // take_while(!= UNUSED): rows are always written compactly
-    const unsigned vm = __ballot_sync(kFullMask, v != kUnusedId);
-    const int cn = __popc(vm & (((vm + 1u) & ~vm) - 1u));  // length of the leading run of valid slots
-    float dt = 0.0f;
-    if (cn > 0) {
-        set_query_from_element(ix, c, dist, i);
-        dt = dist.dists(ix, c, v, cn);  // elements.dists(node_id, &neighbors) (:938)
+    // take_while(!= UNUSED): rows are always written compactly; distances elements.dists(node_id, &neighbors) (:938)
+    int cn = 0;
+    for (uint32_t base = 0; base < node_width; base += 32) {
+        const uint32_t v = (base + lane < node_width) ? __ldcg(row + base + lane) : kUnusedId;
+        const unsigned vm = __ballot_sync(kFullMask, v != kUnusedId);
+        const int run = __popc(vm & (((vm + 1u) & ~vm) - 1u));  // length of the leading run of valid slots
+        if (run > 0) {
+            if (cn == 0) set_query_from_element(ix, c, dist, i);
+            const float dt = dist.dists(ix, c, v, run);
+            if (lane < run) {
+                s.tid[cn + lane] = v;
+                s.td[cn + lane] = dt;
+            }
+        }
+        cn += run;
+        if (run < 32) break;
+    }
+    if (has_extra && lane == 0) {
+        s.tid[cn] = ej;
+        s.td[cn] = ed;
     }
     const int ct = cn + (has_extra ? 1 : 0);
-    const uint32_t my_id = lane < cn ? v : ej;
-    const float my_d = lane < cn ? dt : ed;
+    __syncwarp();
     // candidates.sort_unstable_by_key(|&(_, d)| d) (:945); ties keep their position (the reference's order among
     // equal distances is unspecified)
-    int rank = 0;
-    for (int u = 0; u < ct; ++u) {
-        const float du = __shfl_sync(kFullMask, my_d, u);
-        rank += (du < my_d || (du == my_d && u < lane)) ? 1 : 0;
-    }
-    __syncwarp();
-    if (lane < ct) {
-        s.cid[rank] = my_id;
+    for (int t = lane; t < ct; t += 32) {
+        const float my_d = s.td[t];
+        int rank = 0;
+        for (int u = 0; u < ct; ++u) {
+            const float du = s.td[u];
+            rank += (du < my_d || (du == my_d && u < t)) ? 1 : 0;
+        }
+        s.cid[rank] = s.tid[t];
         s.cd[rank] = my_d;
     }
     __syncwarp();
     const int ns = select_neighbors(ix, c, dist, s, ct, limit);
     // set new neighbors and mark the remaining positions as unused (:950-958)
-    if ((uint32_t)lane < node_width) __stcg(row + lane, lane < ns ? s.sid[lane] : kUnusedId);
+    for (uint32_t t = lane; t < node_width; t += 32) __stcg(row + t, (int)t < ns ? s.sid[t] : kUnusedId);
     __syncwarp();
 }
 
@@ -154,20 +182,22 @@ __device__ __forceinline__ void connect_nodes(const DeviceIndex& ix, WarpCtx& c,
     if (i == j) return;
     const int lane = c.lane;
     uint32_t* row = rows + (size_t)i * stride;
-    const uint32_t v = ((uint32_t)lane < node_width) ? __ldcg(row + lane) : 0u;
-    const unsigned hit = __ballot_sync(kFullMask, ((uint32_t)lane < node_width) && (v == kUnusedId || v == j));
-    if (hit) {
-        if (lane == 0) __stcg(row + (__ffs(hit) - 1), j);
-        __syncwarp();
-    } else {
-        add_and_limit(ix, c, dist, s, rows, stride, node_width, i, true, j, d, (int)node_width);
+    for (uint32_t base = 0; base < node_width; base += 32) {
+        const uint32_t v = (base + lane < node_width) ? __ldcg(row + base + lane) : 0u;
+        const unsigned hit = __ballot_sync(kFullMask, (base + lane < node_width) && (v == kUnusedId || v == j));
+        if (hit) {  // the first free slot, or j is already a neighbour
+            if (lane == 0) __stcg(row + base + (__ffs(hit) - 1), j);
+            __syncwarp();
+            return;
+        }
     }
+    add_and_limit(ix, c, dist, s, rows, stride, node_width, i, true, j, d, (int)node_width);
 }
 
 template <class Dist>
 __device__ __forceinline__ void setup_ctx(const DeviceIndex& ix, WarpCtx& c, LinkScratch& s, unsigned char* smem_raw,
                                           uint32_t stg_rows, uint32_t stg_row_bytes, uint32_t tile_rows,
-                                          uint32_t cand_cap) {
+                                          uint32_t cand_cap, uint32_t node_width = 32) {
     c.lane = threadIdx.x;
     unsigned char* sp = smem_raw;
     c.tile = reinterpret_cast<float*>(sp);
@@ -204,13 +234,18 @@ __device__ __forceinline__ void setup_ctx(const DeviceIndex& ix, WarpCtx& c, Lin
     sp += (size_t)cand_cap * 4;
     s.cd = reinterpret_cast<float*>(sp);
     sp += (size_t)cand_cap * 4;
+    const uint32_t slots = link_node_slots(node_width);
     s.sid = reinterpret_cast<uint32_t*>(sp);
-    sp += 32 * 4;
+    sp += slots * 4;
     s.sd = reinterpret_cast<float*>(sp);
-    sp += 32 * 4;
+    sp += slots * 4;
     s.oid = reinterpret_cast<uint32_t*>(sp);
-    sp += 32 * 4;
+    sp += slots * 4;
     s.od = reinterpret_cast<float*>(sp);
+    sp += slots * 4;
+    s.tid = reinterpret_cast<uint32_t*>(sp);
+    sp += (slots + 8) * 4;
+    s.td = reinterpret_cast<float*>(sp);
 }
 
 // index_element (:805-846) after the candidate search, one warp per element of the batch.
@@ -219,8 +254,8 @@ __global__ void __launch_bounds__(32) build_link_kernel(const DeviceIndex ix, co
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WarpCtx c;
     LinkScratch s;
-    const uint32_t cand_cap = a.cand_stride > 40 ? a.cand_stride : 40;
-    setup_ctx<Dist>(ix, c, s, smem_raw, a.stg_rows, a.stg_row_bytes, a.tile_rows, cand_cap);
+    const uint32_t cand_cap = link_cand_cap(a.cand_stride, a.node_width);
+    setup_ctx<Dist>(ix, c, s, smem_raw, a.stg_rows, a.stg_row_bytes, a.tile_rows, cand_cap, a.node_width);
     Dist dist;
     const int lane = c.lane;
     while (true) {
@@ -268,7 +303,7 @@ __global__ void __launch_bounds__(32) build_link_kernel(const DeviceIndex ix, co
             uint32_t* row = a.rows + (size_t)idx * a.stride;
             const uint32_t first = __ldcg(row);
             if (first == kUnusedId) {
-                if ((uint32_t)lane < a.node_width && lane < ns) __stcg(row + lane, s.oid[lane]);
+                for (int t = lane; t < ns && (uint32_t)t < a.node_width; t += 32) __stcg(row + t, s.oid[t]);
                 __syncwarp();
             } else {
                 for (int t = 0; t < ns; ++t)
@@ -292,7 +327,8 @@ __global__ void __launch_bounds__(32) build_prune_kernel(const DeviceIndex ix, c
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WarpCtx c;
     LinkScratch s;
-    setup_ctx<Dist>(ix, c, s, smem_raw, a.stg_rows, a.stg_row_bytes, a.tile_rows, 40);
+    setup_ctx<Dist>(ix, c, s, smem_raw, a.stg_rows, a.stg_row_bytes, a.tile_rows, link_cand_cap(0, a.node_width),
+                    a.node_width);
     Dist dist;
     while (true) {
         unsigned int w0 = 0;

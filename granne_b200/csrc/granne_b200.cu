@@ -903,7 +903,8 @@ int builder_index_elements(Builder* b, uint32_t layer_m, uint32_t ef, uint64_t a
     int rc = builder_reserve(b, max_batch, ef, num);
     if (rc) return rc;
     GB_CUDA(cudaMemsetAsync(b->d_locks, 0, num * sizeof(int), stream));
-    const size_t link_smem = plan.base_smem + (size_t)std::max<uint32_t>(ef, 40) * 8 + 4 * 32 * 4 + 64;
+    const size_t link_smem = plan.base_smem + gb::link_scratch_bytes(gb::link_cand_cap(ef, b->cfg.num_neighbors),
+                                                                      b->cfg.num_neighbors) + 64;
     uint64_t pos = 0;
     while (pos < total) {
         // nodes already linked into this layer: a batch never exceeds 1/16 of them (its members do not see each other)
@@ -940,7 +941,8 @@ int builder_index_elements(Builder* b, uint32_t layer_m, uint32_t ef, uint64_t a
     }
     // limit number of neighbors (:794-797)
     GB_CUDA(cudaMemsetAsync(b->d_counter, 0, 16, stream));
-    LinkLaunch P{h, {}, plan.base_smem + 40 * 8 + 4 * 32 * 4 + 64, 0, stream, true};
+    LinkLaunch P{h, {}, plan.base_smem + gb::link_scratch_bytes(gb::link_cand_cap(0, b->cfg.num_neighbors),
+                                                               b->cfg.num_neighbors) + 64, 0, stream, true};
     P.a.rows = rows;
     P.a.stride = b->stride;
     P.a.node_width = b->cfg.num_neighbors;
@@ -1317,8 +1319,9 @@ static int builder_new_impl(const granne_b200_build_config* cfg, int element_kin
         *out = nullptr;
         int rc = dev_rows ? GRANNE_B200_OK : check_open_args(elements_bytes, element_kind, embeddings_bytes);
         if (rc) return rc;
-        if (cfg->num_neighbors < 1 || cfg->num_neighbors > 31)
-            return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "num_neighbors must be in 1..31 for the GPU builder");
+        // the on-disk format counts a list's entries in one byte (set_vector.rs:91-99): 255 is the format's limit
+        if (cfg->num_neighbors < 1 || cfg->num_neighbors > 255)
+            return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "num_neighbors must be in 1..255");
         if (cfg->max_search < 1) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "max_search must be >= 1");
         if (!(cfg->layer_multiplier > 1.0f))
             return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "layer_multiplier must be > 1");
@@ -1372,8 +1375,47 @@ int granne_b200_builder_append(granne_b200_builder* b, const void* elements_byte
     try {
         Handle* h = b->h.get();
         gb::DeviceIndex& d = h->dev;
+        if (d.kind == gb::kSumEmbeddings) {
+            // ExtendableElementContainer for SumEmbeddings (src/elements/embeddings/mod.rs:97-100,177-189): the image
+            // holds the new elements' term lists (VariableWidthSliceVector, src/slice_vector/mod.rs:660-676); they
+            // are appended behind the staged ones, the embedding table is unchanged
+            gb::SumElements se;
+            std::string err;
+            if (!gb::parse_sum_elements(static_cast<const uint8_t*>(elements_bytes), elements_len, &se, &err))
+                return fail(GRANNE_B200_ERR_FORMAT, err);
+            const uint64_t add = se.offsets.size() - 1;
+            if (add == 0) return GRANNE_B200_OK;
+            for (uint32_t t : se.terms)
+                if (t >= d.num_vectors) return fail(GRANNE_B200_ERR_FORMAT, "element refers to a missing embedding id");
+            const uint64_t old_n = d.num_elements, new_n = old_n + add;
+            if (new_n >= 0xFFFFFFFFull) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "too many elements");  // :420
+            GB_DEVICE(h->device);
+            GB_CUDA(cudaStreamSynchronize(b->ws->stream));
+            unsigned long long old_terms = 0;
+            if (old_n)
+                GB_CUDA(cudaMemcpy(&old_terms, d.sum_offsets + old_n, 8, cudaMemcpyDeviceToHost));
+            std::vector<unsigned long long> off(add + 1);
+            for (uint64_t i = 0; i <= add; ++i) off[i] = old_terms + se.offsets[i];
+            unsigned long long* doff = nullptr;
+            uint32_t* dterms = nullptr;
+            int rc;
+            if ((rc = dev_alloc(h, &doff, new_n + 1))) return rc;
+            if ((rc = dev_alloc(h, &dterms, (size_t)old_terms + se.terms.size()))) return rc;
+            if (old_n) {
+                GB_CUDA(cudaMemcpy(doff, d.sum_offsets, (size_t)old_n * 8, cudaMemcpyDeviceToDevice));
+                if (old_terms) GB_CUDA(cudaMemcpy(dterms, d.sum_terms, (size_t)old_terms * 4, cudaMemcpyDeviceToDevice));
+            }
+            GB_CUDA(cudaMemcpy(doff + old_n, off.data(), (add + 1) * 8, cudaMemcpyHostToDevice));
+            if (!se.terms.empty())
+                GB_CUDA(cudaMemcpy(dterms + old_terms, se.terms.data(), se.terms.size() * 4, cudaMemcpyHostToDevice));
+            // (the old arrays stay alive in h->allocations: snapshots handed out by get_index may still read them)
+            d.sum_offsets = doff;
+            d.sum_terms = dterms;
+            d.num_elements = new_n;
+            return GRANNE_B200_OK;
+        }
         if (d.kind != gb::kAngularF32 && d.kind != gb::kAngularI8)
-            return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "append supports the angular and angular_int containers");
+            return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "unknown element kind");
         const bool i8 = d.kind == gb::kAngularI8;
         const size_t esz = i8 ? 1 : 4;
         gb::DenseView dv;
@@ -1628,7 +1670,7 @@ int granne_b200_compute_distances(int element_kind, const float* a, const float*
         GB_CUDA(cudaMalloc(&d_err, 4));
         GB_CUDA(cudaMemcpy(d_a, a, (size_t)n * dim * 4, cudaMemcpyHostToDevice));
         GB_CUDA(cudaMemset(d_err, 0, 4));
-        PairLaunch L{h.get(), {}, plan.base_smem + 8 * 8 + 4 * 32 * 4 + 64, 0, nullptr};
+        PairLaunch L{h.get(), {}, plan.base_smem + gb::link_scratch_bytes(8, 32) + 64, 0, nullptr};
         L.a.queries = d_a;
         L.a.n = (uint32_t)n;
         L.a.out = d_out;

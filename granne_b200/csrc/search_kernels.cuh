@@ -695,19 +695,42 @@ struct DistSum {
             const int nb = (k - j0) < rb ? (k - j0) : rb;
             const uint32_t idl = __shfl_sync(kFullMask, my_id, (j0 + c.lane) & 31);  // lane t: candidate j0 + t
             __syncwarp();
-            // get_embedding_internal (embeddings/mod.rs:124-143): ordered sum of the term rows, element-wise
+            // get_embedding_internal (embeddings/mod.rs:124-143): ordered sum of the term rows, element-wise.  Lane t
+            // holds the id of term t; four 32-float chunks of a row are accumulated per pass, so that four independent
+            // 128-byte loads per term are in flight (the adds per element stay in term order: sum_into_f32).
             for (int b = 0; b < nb; ++b) {
                 const uint32_t id = __shfl_sync(kFullMask, idl, b);
                 const unsigned long long tb = ix.sum_offsets[id], te = ix.sum_offsets[id + 1];
+                const uint32_t m = (uint32_t)(te - tb);
                 float* xb = X + b * xstride;
-                for (int i = c.lane; i < dim; i += 32) {
-                    float x = 0.0f;
-                    if (tb < te) {
-                        x = __ldg(emb + (size_t)ix.sum_terms[tb] * stride + i);
-                        for (unsigned long long t = tb + 1; t < te; ++t)
-                            x = __fadd_rn(x, __ldg(emb + (size_t)ix.sum_terms[t] * stride + i));  // sum_into_f32
+                for (int i0 = 0; i0 < dim; i0 += 128) {
+                    const int i = i0 + c.lane;
+                    const bool in0 = i < dim, in1 = i + 32 < dim, in2 = i + 64 < dim, in3 = i + 96 < dim;
+                    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+                    for (uint32_t g = 0; g < m; g += 32) {
+                        const uint32_t gm = (m - g) < 32u ? (m - g) : 32u;
+                        const uint32_t my_term = ((uint32_t)c.lane < gm) ? __ldg(ix.sum_terms + tb + g + c.lane) : 0u;
+                        for (uint32_t t = 0; t < gm; ++t) {
+                            const uint32_t term = __shfl_sync(kFullMask, my_term, t);
+                            const float* row = emb + (size_t)term * stride + i;
+                            const float v0 = in0 ? __ldg(row) : 0.0f;
+                            const float v1 = in1 ? __ldg(row + 32) : 0.0f;
+                            const float v2 = in2 ? __ldg(row + 64) : 0.0f;
+                            const float v3 = in3 ? __ldg(row + 96) : 0.0f;
+                            if (g + t == 0) {  // x = row_0, then x += row_t in order
+                                a0 = v0, a1 = v1, a2 = v2, a3 = v3;
+                            } else {
+                                a0 = __fadd_rn(a0, v0);
+                                a1 = __fadd_rn(a1, v1);
+                                a2 = __fadd_rn(a2, v2);
+                                a3 = __fadd_rn(a3, v3);
+                            }
+                        }
                     }
-                    xb[i] = x;
+                    if (in0) xb[i] = a0;
+                    if (in1) xb[i + 32] = a1;
+                    if (in2) xb[i + 64] = a2;
+                    if (in3) xb[i + 96] = a3;
                 }
             }
             __syncwarp();

@@ -70,6 +70,21 @@ def read_sum_terms(data):
     return [terms[int(offsets[i]):int(offsets[i + 1])].tolist() for i in range(n)]
 
 
+def write_sum_terms(lists):
+    """The inverse of read_sum_terms: VariableWidthSliceVector<ThreeByteInt, FiveByteInt>::write
+    (src/slice_vector/mod.rs:623-634): u64 count | (count + 1) 5-byte offsets | 3-byte ids."""
+    out = bytearray(len(lists).to_bytes(8, "little"))
+    total = 0
+    out += total.to_bytes(5, "little")
+    for l in lists:
+        total += len(l)
+        out += total.to_bytes(5, "little")
+    for l in lists:
+        for t in l:
+            out += int(t).to_bytes(3, "little")
+    return bytes(out)
+
+
 def create_embedding(table, ids, dim=None):
     """SumEmbeddings::create_embedding (src/elements/embeddings/mod.rs:119-143): the first row, then ordered
     element-wise f32 adds of the others (sum_into_f32, src/math.rs:92-116); no ids -> zeros (or [] for an empty table)."""

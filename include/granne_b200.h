@@ -229,7 +229,7 @@ int granne_b200_decode_layer(const void* index_bytes, size_t index_len, uint64_t
 typedef struct granne_b200_build_config {
     float layer_multiplier;        /* 15.0 */
     int64_t expected_num_elements; /* < 0 == None */
-    uint32_t num_neighbors;        /* 30; this implementation supports 1..31 */
+    uint32_t num_neighbors;        /* 30; 1..255 (the file format counts a list in one byte) */
     uint32_t max_search;           /* 200 */
     int32_t reinsert_elements;     /* 1 */
     int32_t show_progress;         /* accepted for compatibility, ignored */
@@ -247,9 +247,11 @@ int granne_b200_builder_new(const granne_b200_build_config* cfg, int element_kin
 int granne_b200_builder_new_device_elements(const granne_b200_build_config* cfg, int element_kind,
                                             const void* d_element_rows, uint64_t num_elements, uint32_t dim,
                                             int device, granne_b200_builder** out);
-/* GranneBuilder::push (src/index/mod.rs:512-531; py GranneBuilder.append, py/src/lib.rs:474-476) for the angular and
- * angular_int containers: appends the rows of an elements file image (same width) to the builder's container; they are
- * indexed by the next build.  Not concurrent with other calls on `b`. */
+/* GranneBuilder::push (src/index/mod.rs:512-531; py GranneBuilder.append, py/src/lib.rs:474-476): appends the
+ * elements of an elements file image of the builder's own kind to its container; they are indexed by the next build.
+ * angular / angular_int: rows of the same width (ExtendableElementContainer for Vectors, dense_vector.rs:120-136);
+ * embeddings: term lists over the unchanged embedding table (SumEmbeddings::push, embeddings/mod.rs:97-100,177-189).
+ * Not concurrent with other calls on `b`. */
 int granne_b200_builder_append(granne_b200_builder* b, const void* elements_bytes, size_t elements_len);
 /* Builder::build_partial(num_elements) (:374-402); num_elements == 0 means Builder::build() (all elements, :366-368). */
 int granne_b200_builder_build(granne_b200_builder* b, uint64_t num_elements);

@@ -36,13 +36,16 @@ def _self_recall(index, rows, max_search):
     return float((ids[:, 0] == np.arange(rows.shape[0])).mean())
 
 
-@pytest.mark.parametrize("kind,n,dim", [("angular", 1500, 28), ("angular_int", 500, 32), ("angular", 3000, 128)])
-def test_build_and_search_like_the_reference(oracle, kind, n, dim):
+@pytest.mark.parametrize("kind,n,dim,m", [("angular", 1500, 28, 20), ("angular_int", 500, 32, 20),
+                                          ("angular", 3000, 128, 20), ("angular", 2500, 32, 48),
+                                          ("angular_int", 1200, 40, 70)])
+def test_build_and_search_like_the_reference(oracle, kind, n, dim, m):
     # build_and_search_float / build_and_search_int8 (src/index/tests.rs:41-62,114-132): M=20, max_search=20,
-    # then every element must find itself with max_search = 10
+    # then every element must find itself with max_search = 10.  BuildConfig has no cap on num_neighbors
+    # (src/index/mod.rs:198-291): rows wider than a warp (48, 70) go through the same kernels 32 slots at a time.
     raw = random_vectors(n, dim, seed=n)
     eb = granne_b200.elements_from_raw(kind, raw).tobytes()
-    b = granne_b200.GranneBuilder(kind, eb, num_neighbors=20, max_search=20)
+    b = granne_b200.GranneBuilder(kind, eb, num_neighbors=m, max_search=max(20, m))
     b.build()
     assert len(b) == n
     expect_layers = []
@@ -57,7 +60,7 @@ def test_build_and_search_like_the_reference(oracle, kind, n, dim):
     assert _self_recall(index, rows, 10) > 0.95
     # degrees respect num_neighbors (and num_neighbors / 2 on upper layers, :665-668)
     for layer in range(index.num_layers()):
-        limit = 20 if layer == index.num_layers() - 1 else 10
+        limit = m if layer == index.num_layers() - 1 else m // 2
         for i in range(0, index.layer_len(layer), 37):
             nb = index.get_neighbors(i, layer)
             assert len(nb) <= limit and len(set(nb)) == len(nb) and i not in nb
@@ -208,6 +211,45 @@ def test_append_then_build_incrementally(oracle, kind):
     assert np.array_equal(ref[0], got[0]) and np.array_equal(ref[1].view(np.uint32), got[1].view(np.uint32))
     with pytest.raises(granne_b200.GranneError):
         b._pending.append(np.zeros(7, dtype=np.float32))           # wrong width is rejected by the library
+        b._flush()
+    for h in (snap, index, b):
+        h.close()
+
+
+def test_append_to_an_embeddings_builder(oracle):
+    """ExtendableElementContainer for SumEmbeddings (src/elements/embeddings/mod.rs:97-100,177-189): elements (lists of
+    embedding ids) pushed after a first build are indexed by the next one; the container then equals the one built in
+    one go, and the oracle searches the resulting index identically."""
+    from granne_b200 import words as W
+    from helpers.data import random_sum_embeddings
+
+    dim, n_emb, n = 24, 120, 700
+    el = random_sum_embeddings(oracle, dim, n_emb, n, seed=8)
+    whole, emb = el.to_bytes(0), el.to_bytes(1)
+    lists = W.read_sum_terms(whole)
+    assert W.write_sum_terms(lists) == whole                      # the writer is the exact inverse of the reader
+    first = W.write_sum_terms(lists[:400])
+    b = granne_b200.GranneBuilder("embeddings", first, emb, num_neighbors=16, max_search=30)
+    b.build()
+    snap = b.get_index()
+    assert len(b) == 400
+    for l in lists[400:]:
+        b.append(l)
+    assert b.num_elements() == n and len(b) == 400                # pushed, not yet indexed
+    b.build()
+    assert len(b) == n and len(snap) == 400
+    index = b.get_index()
+    for i in (0, 399, 400, 555, n - 1):
+        assert np.array_equal(index.get_element(i), el.get(i))
+    assert bytes(index.elements_bytes()) == whole
+    g = oracle.Granne.from_bytes(index.index_bytes(), el)
+    q = random_vectors(64, dim, seed=9)
+    ref = g.search_batch(q, 40, 10, with_stats=True)
+    got = index.search_batch(q, 40, 10, with_stats=True)
+    assert np.array_equal(ref[0], got[0]) and np.array_equal(ref[1].view(np.uint32), got[1].view(np.uint32))
+    assert np.array_equal(ref[3][:, :3], got[3][:, :3])
+    with pytest.raises(granne_b200.GranneError):
+        b.append([n_emb + 5])                                      # a missing embedding id is rejected by the library
         b._flush()
     for h in (snap, index, b):
         h.close()

@@ -21,11 +21,13 @@ granne_b200.load_library()
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(0)
 tables = bench.device_tables(torch, dev, a, a.n)
-el = bench.make_elements_device(torch, granne_b200, dev, a, a.n, bench.DATA_SEED, tables)
-p, _, prov = bench.build_or_load_index(torch, granne_b200, a, dev, el, bench.DATA_SEED)
-del el
-torch.cuda.empty_cache()
-tq = bench.make_queries_device(torch, dev, a, nq, bench.QUERY_SEED, tables)
+cont = bench.make_container(torch, granne_b200, dev, a, a.n, bench.DATA_SEED, tables)
+p, _, prov = bench.build_or_load_index(torch, granne_b200, a, dev, cont, bench.DATA_SEED)
+if a.kind == "embeddings":
+    tq = torch.from_numpy(cont.queries(nq, bench.QUERY_SEED)).to(dev)
+else:
+    tq = bench.make_queries_device(torch, dev, a, nq, bench.QUERY_SEED, tables)
+cont.free()
 stats = torch.zeros((nq, 4), dtype=torch.int64, device=dev)
 out = None
 for it in range(iters):
