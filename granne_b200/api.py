@@ -59,6 +59,7 @@ def load_library():
         "granne_b200_search_batch_device": (i32, [vp, vp, sz, i32, u32, u32, vp, vp, vp, vp, vp]),
         "granne_b200_search_batch_device_gather": (i32, [vp, vp, sz, i32, u32, u32, vp, vp, vp, vp]),
         "granne_b200_stream_status": (i32, [vp]),
+        "granne_b200_release_stream": (i32, [vp, vp]),
         "granne_b200_merge_topk_device": (i32, [i32, vp, vp, vp, sz, sz, u32, vp, vp, vp]),
         "granne_b200_inspect_index": (i32, [vp, sz, vp, vp, vp, vp, sz]),
         "granne_b200_decode_layer": (i32, [vp, sz, u64, vp, sz]),
@@ -421,6 +422,11 @@ class Granne:
 
     def stream_status(self):
         _check(load_library().granne_b200_stream_status(self._h))
+
+    def release_stream(self, stream):
+        """Returns the workspace the library keeps for a caller stream (a raw cudaStream_t or a torch stream)."""
+        raw = getattr(stream, "cuda_stream", stream)
+        _check(load_library().granne_b200_release_stream(self._h, C.c_void_p(raw)))
 
     def launch_count(self):
         return int(load_library().granne_b200_launch_count(self._h))

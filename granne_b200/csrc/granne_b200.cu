@@ -1200,6 +1200,29 @@ int granne_b200_search_batch_device_gather(granne_b200_index* h, const void* d_q
                               d_out_counts, d_out_stats, cuda_stream, gather);
 }
 
+// The device-pointer API keeps one workspace per distinct caller stream (status words, visited tables: up to
+// ~1 GB at large max_search).  A caller that retires a stream hands its workspace back with this call (it synchronises
+// the stream first); granne_b200_close releases everything anyway.
+int granne_b200_release_stream(granne_b200_index* h, void* cuda_stream) {
+    if (!h) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "index handle is null");
+    GB_DEVICE(h->device);
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    std::unique_ptr<Workspace> w;
+    {
+        std::lock_guard<std::mutex> g(h->pool_mu);
+        auto it = h->stream_ws.find(stream);
+        if (it == h->stream_ws.end()) return GRANNE_B200_OK;
+        w = std::move(it->second);
+        h->stream_ws.erase(it);
+    }
+    GB_CUDA(cudaStreamSynchronize(stream));
+    int e[4] = {0, 0, 0, 0};
+    GB_CUDA(cudaMemcpy(e, w->d_error, sizeof(e), cudaMemcpyDeviceToHost));
+    h->sticky_error.fetch_or(e[0]);  // reported by the next granne_b200_stream_status
+    ws_destroy(w.get());
+    return GRANNE_B200_OK;
+}
+
 int granne_b200_stream_status(granne_b200_index* h) {
     if (!h) return fail(GRANNE_B200_ERR_INVALID_ARGUMENT, "index handle is null");
     GB_DEVICE(h->device);

@@ -161,6 +161,11 @@ int granne_b200_search_batch_device_gather(granne_b200_index* h, const void* d_q
                                            const granne_b200_peer_gather* gather, uint32_t* d_out_counts,
                                            uint64_t* d_out_stats, void* cuda_stream);
 
+/* The device-pointer calls keep one workspace per distinct caller stream (status words, per-warp visited tables) until
+ * granne_b200_close.  A caller that retires a stream returns its workspace with this call (it synchronises the stream;
+ * an error raised by its last batches is reported by the next granne_b200_stream_status). */
+int granne_b200_release_stream(granne_b200_index* h, void* cuda_stream);
+
 /* After synchronising a stream used with granne_b200_search_batch_device: GRANNE_B200_OK, or the first error
  * (ERR_NOT_FINITE / ERR_CAPACITY) any query of the calls issued since the previous check raised. */
 int granne_b200_stream_status(granne_b200_index* h);

@@ -106,6 +106,14 @@ def test_search_batch_device_validates_its_tensors(oracle):
             idx.search_batch_device(bad, 30, 5)
     with pytest.raises(ValueError):
         idx.search_batch_device(q, 30, 5, out=(ids.long(), d, c))
+    # a retired stream hands its workspace back; the handle keeps working on other streams
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        ids3, d3, _ = idx.search_batch_device(q, 30, 5, stream=side.cuda_stream)
+    idx.release_stream(side)
+    assert torch.equal(ids, ids3) and torch.equal(d, d3)
+    idx.release_stream(side)          # releasing twice is harmless
+    idx.stream_status()
     idx.close()
     b.close()
 
