@@ -403,6 +403,20 @@ class ClockSampler:
                 break
             time.sleep(0.0003)
 
+    def sample_now(self):
+        """one sample taken by the caller itself (while the GPU is draining the issued steps): a very short timed
+        region can end before the sampler thread has been scheduled once"""
+        if self.h is None:
+            return
+        try:
+            nv = self.nv
+            reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(
+                nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+            self.rows.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+            self.bits |= int(reasons(self.h))
+        except Exception:
+            pass
+
     def start(self):
         if self.h is None:
             return
@@ -836,6 +850,8 @@ def main():
     for st in streams:
         torch.cuda.current_stream(dev).wait_stream(st)
     e1.record(torch.cuda.current_stream(dev))
+    if rank == 0:
+        sampler.sample_now()  # everything is issued, the GPU is still inside the timed region
     sync_all()
     torch.cuda.nvtx.range_pop()
     if world > 1:
