@@ -391,6 +391,8 @@ LaunchPlan make_plan(const Handle* h, uint32_t max_search) {
     p.staged = is_staged_kind(d);
     p.tile_rows = d.kind == gb::kAngularI8 ? 0u : ((p.staged || d.kind == gb::kSumEmbeddings) ? 8u : 32u);
     const bool generic_staged = is_generic_f32_staged(d);
+    if (is_templated_f32(d))  // the ordered-sum tile has one row per staged candidate row of a batch
+        p.tile_rows = std::min<uint32_t>(8u, std::max<uint32_t>(4, ((unsigned)GB_STG_BYTES / (d.full * 128u)) & ~3u));
     size_t base = gb::tile_bytes_for_rows(p.tile_rows) + 16 + ((qbytes + 15u) & ~15u) * (d.kind == gb::kSumEmbeddings ? 2 : 1);
     p.stg_rows = 0;
     p.stg_row_bytes = 0;

@@ -350,14 +350,18 @@ struct DistF32 {
     // Gather: one cp.async per row (per 32-chunk group): lane l copies the V*4 bytes of the permuted row that lane l
     // itself consumes, so a row costs SHFL + address + LDGSTS, all rows of the batch are in flight together, no data
     // registers are held and no cross-lane barrier is needed before the partial sums.
+    // `ids_smem` (may be null): the same candidate ids, compacted in shared memory — the search loop has them there
+    // anyway, and a broadcast LDS per row is cheaper than a shuffle with its divergence check.
     template <class Hook>
-    __device__ __forceinline__ float dists(const DeviceIndex& ix, WarpCtx& c, uint32_t my_id, int k, Hook&& after_wait) {
+    __device__ __forceinline__ float dists(const DeviceIndex& ix, WarpCtx& c, uint32_t my_id, int k, Hook&& after_wait,
+                                           const uint32_t* ids_smem = nullptr) {
         float d = 0.0f;
         if (FULL > 0) {
             const uint32_t stride_bytes = ix.row_stride * 4u;
             constexpr uint32_t row_bytes = FULL * 128u;  // the permuted chunk part of a row
             constexpr uint32_t lane_bytes = V * 4u;
             const char* src0 = static_cast<const char*>(ix.vectors) + c.lane * lane_bytes;
+            asm volatile("" : "+l"(src0));  // keep the per-lane base in one register pair (one IMAD.WIDE per row)
             const uint32_t dst0 = smem_u32(c.stg) + c.lane * lane_bytes;
             const unsigned char* mine = c.stg + c.lane * lane_bytes;
             const int rb = (int)c.stg_rows;
@@ -367,7 +371,7 @@ struct DistF32 {
 #pragma unroll
                 for (int b = 0; b < 8; ++b) {
                     if (b >= nb) break;
-                    const uint32_t idb = __shfl_sync(kFullMask, my_id, j0 + b);
+                    const uint32_t idb = ids_smem ? ids_smem[j0 + b] : __shfl_sync(kFullMask, my_id, j0 + b);
                     const char* src = src0 + (size_t)idb * stride_bytes;
 #pragma unroll
                     for (int g = 0; g < G; ++g)
@@ -484,7 +488,8 @@ struct DistF32Generic {
         return d;
     }
     template <class Hook>
-    __device__ __forceinline__ float dists(const DeviceIndex& ix, WarpCtx& c, uint32_t my_id, int k, Hook&& after_wait) {
+    __device__ __forceinline__ float dists(const DeviceIndex& ix, WarpCtx& c, uint32_t my_id, int k, Hook&& after_wait,
+                                           const uint32_t* = nullptr) {
         const float d = dists(ix, c, my_id, k);
         after_wait();
         return d;
@@ -607,7 +612,8 @@ struct DistI8 {
         return finish(c, my_r, my_dx, lane < k);
     }
     template <class Hook>
-    __device__ __forceinline__ float dists(const DeviceIndex& ix, WarpCtx& c, uint32_t my_id, int k, Hook&& after_wait) {
+    __device__ __forceinline__ float dists(const DeviceIndex& ix, WarpCtx& c, uint32_t my_id, int k, Hook&& after_wait,
+                                           const uint32_t* = nullptr) {
         const float d = dists(ix, c, my_id, k);
         after_wait();
         return d;
@@ -678,7 +684,8 @@ struct DistSum {
     // 32-lane sums of a whole batch run in parallel (lane b sums candidate b) instead of two 32-step shuffle chains
     // per candidate.
     template <class Hook>
-    __device__ __forceinline__ float dists(const DeviceIndex& ix, WarpCtx& c, uint32_t my_id, int k, Hook&& after_wait) {
+    __device__ __forceinline__ float dists(const DeviceIndex& ix, WarpCtx& c, uint32_t my_id, int k, Hook&& after_wait,
+                                           const uint32_t* = nullptr) {
         const float d = dists(ix, c, my_id, k);
         after_wait();
         return d;
@@ -1242,7 +1249,7 @@ __device__ __forceinline__ void search_layer_fast(const DeviceIndex& ix, WarpCtx
             const unsigned nm = __ballot_sync(kFullMask, is_new);
             const int k = __popc(nm);
             vis_count += k;
-            if (__any_sync(kFullMask, ovf) || vis_count > vis_limit) {
+            if (ovf || vis_count > vis_limit) {  // (ovf is warp-uniform: it is set on a uniform path of the probe loop)
                 c.status |= kStatusOverflow;
                 *out_n = n;
                 return;
@@ -1265,7 +1272,7 @@ __device__ __forceinline__ void search_layer_fast(const DeviceIndex& ix, WarpCtx
                     cp_async_commit();  // its own group: the consumer waits for all groups but the next pop's
                     spec_bk = true;
                 }
-            });
+            }, c.ids);
             if (__any_sync(kFullMask, c.status & kStatusNotFinite)) {
                 c.status |= kStatusNotFinite;
                 *out_n = n;
