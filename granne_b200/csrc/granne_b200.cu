@@ -351,6 +351,7 @@ int read_file(const char* path, std::vector<uint8_t>* out) {
 // ---- launch configuration -----------------------------------------------------------------------------------------
 struct LaunchPlan {
     uint32_t list_cap, vis_slots, vis_upper;
+    uint32_t vis_retry;  // visited slots per CTA of the retry pass
     int rows;           // fast list rows R (capacity 32*R), 0 = generic list
     uint32_t stg_rows;  // candidate rows per bulk-copy batch (staged distance engines only)
     uint32_t stg_row_bytes;
@@ -386,7 +387,11 @@ LaunchPlan make_plan(const Handle* h, uint32_t max_search) {
     p.list_cap = p.rows ? 32u * p.rows : std::max<uint32_t>(32, (max_search + 16 + 31) & ~31u);
     const uint32_t deg = h->layer_max_degree.empty() ? 1 : std::max<uint32_t>(8, h->layer_max_degree.back());
     uint64_t want = std::max<uint64_t>(1024, (uint64_t)max_search * std::min<uint32_t>(deg, 64));
-    want = ((want + 31) & ~31ull) * h->vis_scale.load();
+    want = (want + 31) & ~31ull;
+    // the retry pass gets 8x the base table, the fast pass base x scale (both capped at 4 MB per warp)
+    const uint64_t cap_slots = 1ull << 20;
+    p.vis_retry = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(want * 8, want), std::max<uint64_t>(cap_slots, want));
+    want = std::min<uint64_t>(want * h->vis_scale.load(), std::max<uint64_t>(cap_slots, want));
     const uint32_t qbytes = (d.kind == gb::kAngularI8) ? d.row_stride : ((d.dim + 3u) & ~3u) * 4u;
     p.staged = is_staged_kind(d);
     p.tile_rows = d.kind == gb::kAngularI8 ? 0u : ((p.staged || d.kind == gb::kSumEmbeddings) ? 8u : 32u);
@@ -518,7 +523,7 @@ int launch_kernels(Handle* h, Workspace* w, gb::SearchArgs a, const LaunchPlan& 
         r.work_counter = w->d_counters + 1;
         r.gate_in = w->d_counters + 3;
         r.gate_out = w->d_counters + 4;
-        r.vis_slots = plan.vis_slots * 8u;
+        r.vis_slots = std::max(plan.vis_slots, plan.vis_retry);
         r.vis_slots_upper = plan.vis_upper;
         const unsigned rgrid = (unsigned)std::min<unsigned long long>(a.nq, (unsigned long long)h->num_sms * 4);
         const size_t need = (size_t)h->num_sms * 4 * r.vis_slots;

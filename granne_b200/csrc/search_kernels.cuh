@@ -1189,6 +1189,9 @@ __device__ __forceinline__ void search_layer_fast(const DeviceIndex& ix, WarpCtx
         {
             const unsigned rest = sel_mask & (sel_mask - 1);
             if (rest && width <= 32u) {
+                // the slot written now was last written two pops ago; if no distance phase (and so no wait) happened
+                // since, that copy could still be in flight and land AFTER this one — wait for all but the last group
+                cp_async_wait_but_last();
                 spec_slot ^= 1u;
                 spec_id = Li[base_sel + __ffs(rest) - 1];
                 if ((uint32_t)lane < width)
