@@ -4,7 +4,9 @@
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / `--impl reference` legs may load this
 // library, and only as the checker / CPU baseline.  Nothing under granne_b200/ links, imports or calls it.
 //
-// Parity status: the reference is Rust (granne 0.5.2); there is no rustc/cargo in this image, so the reference
+// Parity status: PARITY UNPINNED against a run of the reference — pinned only to the reference's own known-answer
+// tests (below) and, for the Stream VByte bytes, to an independent third statement
+// (tests/test_stream_vbyte_independent.py).  The reference is Rust (granne 0.5.2); there is no rustc/cargo in this image, so the reference
 // itself cannot be compiled or run here, and its own tests use unseeded random data (src/test_helper.rs:3-18), so
 // no golden *search results* exist.  The restatement is pinned against every known-answer test the reference holds
 // for this path (tests/test_oracle_kat.py): layer sizes (src/index/tests.rs:305-335), delta coding
