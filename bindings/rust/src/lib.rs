@@ -18,6 +18,10 @@ pub struct RawIndex {
 pub struct RawBuilder {
     _private: [u8; 0],
 }
+#[repr(C)]
+pub struct RawMulti {
+    _private: [u8; 0],
+}
 
 /// `granne_b200_build_config` — `granne::BuildConfig` (`src/index/mod.rs:198-231`).
 #[repr(C)]
@@ -67,6 +71,19 @@ extern "C" {
     fn granne_b200_builder_layer_len(b: *const RawBuilder, layer: u64) -> u64;
     fn granne_b200_builder_write_index(b: *mut RawBuilder, out: *mut c_void, cap: usize, out_len: *mut usize) -> c_int;
     fn granne_b200_builder_get_index(b: *mut RawBuilder, out: *mut *mut RawIndex) -> c_int;
+
+    fn granne_b200_multi_open(
+        mode: c_int, devices: *const c_int, num_devices: usize, element_kind: c_int, index: *const *const c_void,
+        index_len: *const usize, elements: *const *const c_void, elements_len: *const usize, num_shards: usize,
+        embeddings: *const c_void, embeddings_len: usize, out: *mut *mut RawMulti,
+    ) -> c_int;
+    fn granne_b200_multi_close(m: *mut RawMulti);
+    fn granne_b200_multi_len(m: *const RawMulti) -> u64;
+    fn granne_b200_multi_shard_base(m: *const RawMulti, s: usize) -> u64;
+    fn granne_b200_multi_search_batch(
+        m: *mut RawMulti, queries: *const c_void, nq: usize, query_format: c_int, max_search: u32, num_neighbors: u32,
+        out_ids: *mut u64, out_dists: *mut f32, out_counts: *mut u32,
+    ) -> c_int;
 }
 
 pub const ANGULAR: c_int = 0; // angular::Vectors
@@ -284,5 +301,61 @@ impl GpuGranneBuilder {
 impl Drop for GpuGranneBuilder {
     fn drop(&mut self) {
         unsafe { granne_b200_builder_free(self.b) }
+    }
+}
+
+pub const MODE_REPLICATED: c_int = 0; // one index on every device, query batches sliced
+pub const MODE_RANGE_PARTITIONED: c_int = 1; // one independent index per shard, merged by (distance, global id)
+
+/// Several GPUs of this process behind one handle (`granne_b200_multi_*`): `Granne::from_bytes` + `search` with the
+/// index replicated on every device or range-partitioned into independent shards (granne's own sharding of the
+/// element set, `src/elements/embeddings/parsing.rs:63-100`; merge order of `into_sorted_vec`, `src/index/mod.rs:1036`).
+pub struct GpuMultiGranne {
+    m: *mut RawMulti,
+    dim: usize,
+}
+unsafe impl Send for GpuMultiGranne {}
+unsafe impl Sync for GpuMultiGranne {}
+
+impl GpuMultiGranne {
+    /// `shards`: one `(index bytes, elements bytes)` pair (replicated) or one per shard (range-partitioned);
+    /// angular f32 elements (`dim` floats per row).
+    pub fn open(mode: c_int, shards: &[(&[u8], &[u8])], devices: &[i32], dim: usize) -> Self {
+        let ip: Vec<*const c_void> = shards.iter().map(|s| s.0.as_ptr() as *const c_void).collect();
+        let il: Vec<usize> = shards.iter().map(|s| s.0.len()).collect();
+        let ep: Vec<*const c_void> = shards.iter().map(|s| s.1.as_ptr() as *const c_void).collect();
+        let el: Vec<usize> = shards.iter().map(|s| s.1.len()).collect();
+        let dv: Vec<c_int> = devices.iter().map(|&d| d as c_int).collect();
+        let mut m = std::ptr::null_mut();
+        check(unsafe {
+            granne_b200_multi_open(mode, dv.as_ptr(), dv.len(), ANGULAR, ip.as_ptr(), il.as_ptr(), ep.as_ptr(),
+                                   el.as_ptr(), shards.len(), std::ptr::null(), 0, &mut m)
+        });
+        GpuMultiGranne { m, dim }
+    }
+    pub fn len(&self) -> usize {
+        unsafe { granne_b200_multi_len(self.m) as usize }
+    }
+    pub fn shard_base(&self, s: usize) -> usize {
+        unsafe { granne_b200_multi_shard_base(self.m, s) as usize }
+    }
+    /// `Granne::search` for a batch of normalised vectors; ids are global.
+    pub fn search_batch(&self, elements: &[f32], max_search: usize, num_neighbors: usize) -> Vec<Vec<(usize, f32)>> {
+        let nq = elements.len() / self.dim;
+        let (mut ids, mut d, mut c) = (vec![0u64; nq * num_neighbors], vec![0f32; nq * num_neighbors], vec![0u32; nq]);
+        check(unsafe {
+            granne_b200_multi_search_batch(self.m, elements.as_ptr() as *const c_void, nq, QUERY_ELEMENT,
+                                           max_search as u32, num_neighbors as u32, ids.as_mut_ptr(), d.as_mut_ptr(),
+                                           c.as_mut_ptr())
+        });
+        (0..nq)
+            .map(|i| (0..c[i] as usize).map(|j| (ids[i * num_neighbors + j] as usize, d[i * num_neighbors + j])).collect())
+            .collect()
+    }
+}
+
+impl Drop for GpuMultiGranne {
+    fn drop(&mut self) {
+        unsafe { granne_b200_multi_close(self.m) }
     }
 }

@@ -242,6 +242,81 @@ private:
     int device_ = 0;
 };
 
+// Several GPUs of this process behind one handle (granne_b200_multi_*): `Granne::from_bytes` + `search` with the index
+// replicated on every device (query batches are sliced) or range-partitioned into independent shards (every shard is
+// searched, results merged by (distance, global id) — the order of into_sorted_vec, src/index/mod.rs:1036).
+class MultiGranne {
+public:
+    using Result = std::vector<std::pair<uint64_t, float>>;  // (global id, distance)
+    MultiGranne() = default;
+    MultiGranne(const MultiGranne&) = delete;
+    MultiGranne& operator=(const MultiGranne&) = delete;
+    MultiGranne(MultiGranne&& o) noexcept { std::swap(h_, o.h_); std::swap(dim_, o.dim_); std::swap(kind_, o.kind_); }
+    ~MultiGranne() { if (h_) granne_b200_multi_close(h_); }
+
+    static MultiGranne replicated(const std::vector<uint8_t>& index, const Elements& elements,
+                                  const std::vector<int>& devices) {
+        const void* ip[1] = {index.data()};
+        const size_t il[1] = {index.size()};
+        const void* ep[1] = {elements.bytes.data()};
+        const size_t el[1] = {elements.bytes.size()};
+        MultiGranne m;
+        check(granne_b200_multi_open(GRANNE_B200_MODE_REPLICATED, devices.data(), devices.size(),
+                                     static_cast<int>(elements.kind), ip, il, ep, el, 1,
+                                     elements.embeddings.empty() ? nullptr : elements.embeddings.data(),
+                                     elements.embeddings.size(), &m.h_));
+        m.dim_ = elements.dim();
+        m.kind_ = elements.kind;
+        return m;
+    }
+    // one (index, elements) pair per shard; shard s lives on devices[s % devices.size()]
+    static MultiGranne partitioned(const std::vector<std::vector<uint8_t>>& indexes, const std::vector<Elements>& shards,
+                                   const std::vector<int>& devices) {
+        if (indexes.size() != shards.size() || shards.empty())
+            throw Error(GRANNE_B200_ERR_INVALID_ARGUMENT, "one index per shard");
+        std::vector<const void*> ip, ep;
+        std::vector<size_t> il, el;
+        for (size_t s = 0; s < shards.size(); ++s) {
+            ip.push_back(indexes[s].data());
+            il.push_back(indexes[s].size());
+            ep.push_back(shards[s].bytes.data());
+            el.push_back(shards[s].bytes.size());
+        }
+        MultiGranne m;
+        check(granne_b200_multi_open(GRANNE_B200_MODE_RANGE_PARTITIONED, devices.data(), devices.size(),
+                                     static_cast<int>(shards[0].kind), ip.data(), il.data(), ep.data(), el.data(),
+                                     shards.size(), shards[0].embeddings.empty() ? nullptr : shards[0].embeddings.data(),
+                                     shards[0].embeddings.size(), &m.h_));
+        m.dim_ = shards[0].dim();
+        m.kind_ = shards[0].kind;
+        return m;
+    }
+    uint64_t len() const { return granne_b200_multi_len(h_); }
+    size_t num_parts() const { return granne_b200_multi_num_parts(h_); }
+    uint64_t shard_base(size_t s) const { return granne_b200_multi_shard_base(h_, s); }
+
+    // search(&Vector::from(raw), max_search, num_neighbors) for nq raw f32 queries (nq x dim, row-major)
+    std::vector<Result> search_batch_raw(const std::vector<float>& queries, size_t max_search,
+                                         size_t num_neighbors) const {
+        const size_t nq = dim_ ? queries.size() / dim_ : 0;
+        std::vector<uint64_t> ids(nq * num_neighbors);
+        std::vector<float> d(nq * num_neighbors);
+        std::vector<uint32_t> c(nq);
+        check(granne_b200_multi_search_batch(h_, queries.data(), nq, GRANNE_B200_QUERY_RAW_F32,
+                                             static_cast<uint32_t>(max_search), static_cast<uint32_t>(num_neighbors),
+                                             ids.data(), d.data(), c.data()));
+        std::vector<Result> out(nq);
+        for (size_t i = 0; i < nq; ++i)
+            for (uint32_t j = 0; j < c[i]; ++j) out[i].emplace_back(ids[i * num_neighbors + j], d[i * num_neighbors + j]);
+        return out;
+    }
+
+private:
+    granne_b200_multi* h_ = nullptr;
+    uint64_t dim_ = 0;
+    ElementKind kind_ = ElementKind::Angular;
+};
+
 // granne::BuildConfig (src/index/mod.rs:198-291): `BuildConfig::default().num_neighbors(20).max_search(5)`
 class BuildConfig {
 public:

@@ -167,6 +167,34 @@ static int gpu() {
         const float dab = gb::compute_distance(K::Angular, a, b);
         REQUIRE(dab > 0.0f && dab < 2.0f && dab == gb::compute_distance(K::Angular, b, a));
     }
+    {  // several GPUs (here: cuda:0 named twice) behind one handle: same answers as the single-device index
+        const size_t n = 1200, dim = 24;
+        const std::vector<float> raw = random_rows(n, dim, 9);
+        const gb::Elements elements = gb::Elements::from_raw(K::Angular, raw.data(), n, dim);
+        gb::GranneBuilder builder(gb::BuildConfig().num_neighbors(12).max_search(30), elements);
+        builder.build();
+        const gb::Granne index = builder.get_index();
+        const std::vector<uint8_t> image = index.write_index();
+        const gb::MultiGranne multi = gb::MultiGranne::replicated(image, elements, {0, 0});
+        REQUIRE(multi.len() == n && multi.num_parts() == 2);
+        const std::vector<float> q = random_rows(37, dim, 10);
+        const std::vector<gb::MultiGranne::Result> got = multi.search_batch_raw(q, 30, 5);
+        REQUIRE(got.size() == 37);
+        for (size_t i = 0; i < got.size(); ++i) {
+            const gb::SearchResult want = index.search_raw(std::vector<float>(q.begin() + i * dim, q.begin() + (i + 1) * dim), 30, 5);
+            REQUIRE(want.size() == got[i].size());
+            for (size_t j = 0; j < want.size(); ++j)
+                REQUIRE(want[j].first == got[i][j].first && want[j].second == got[i][j].second);
+        }
+        // two shards = the same index twice: ids of the second copy are offset by n, every hit appears twice
+        const gb::MultiGranne parts = gb::MultiGranne::partitioned({image, image}, {elements, elements}, {0});
+        REQUIRE(parts.len() == 2 * n && parts.shard_base(1) == n);
+        const std::vector<gb::MultiGranne::Result> two = parts.search_batch_raw(q, 30, 4);
+        for (size_t i = 0; i < two.size(); ++i) {
+            REQUIRE(two[i].size() == 4);
+            REQUIRE(two[i][1].first == two[i][0].first + n && two[i][1].second == two[i][0].second);
+        }
+    }
     std::printf("gpu ok\n");
     return 0;
 }
