@@ -1,7 +1,8 @@
 """A/B harness for kernel variants (run on the GPU box in ONE gpurun call).
 
 Here (no GPU):   python -c "from granne_b200 import build; build.build_variant('w28', ['GB_MIN_BLOCKS=28', 'GB_STG_BYTES=2048'])"
-On the box:      python tools/ab_bench.py granne_b200/libgranne_b200.so granne_b200/libgranne_b200_w28.so
+On the box:      python tools/ab_bench.py granne_b200/libgranne_b200.so granne_b200/libgranne_b200_w28.so --config c2
+                 (extra arguments go to bench.py; without --config it runs the 100M default, ~5 min per library)
 
 For every library: the bit-exact parity subset (tests/test_parity_gpu.py + tests/test_golden.py) must pass, then bench.py
 runs with that library (GRANNE_B200_LIB) and the JSON line is collected.  Prints one table; writes gpurun_out/ab_bench.jsonl.
