@@ -895,7 +895,9 @@ def main():
     # ---- end to end through the public host API ------------------------------------------------------------------------
     # persistent worker threads (started and parked on a barrier BEFORE t0), each issuing whole batches through
     # granne_b200_search_batch: memcpy into pinned staging, H2D, kernels, one packed D2H, memcpy out
-    nthreads = max(1, min(a.streams, 8))
+    # client concurrency: 8..16 host threads, the count that splits the timed steps most evenly (20 steps -> 10
+    # threads x 2 calls instead of 8 threads of which half make a third call while the others idle)
+    nthreads = max(1, min(a.steps, min(range(8, 17), key=lambda t: (-(-a.steps // t) * t - a.steps, t))))
     h2d = a.nq * a.dim * 4
     d2h = a.nq * a.k * 8 + a.nq * 4 + 16
 
