@@ -16,6 +16,7 @@
  *  - ids are u32 on this boundary (granne limits an index to 2^32-2 elements: src/lib.rs:7, src/index/mod.rs:27-28,420).
  *  - a handle may be used from several host threads for concurrent search calls; open/close must not race with them.
  *  - the CUDA device is mandatory: there is no CPU fallback behind this ABI.
+ *  - every call runs on its handle's device and restores the calling thread's current CUDA device before it returns.
  */
 #ifndef GRANNE_B200_H
 #define GRANNE_B200_H
@@ -27,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GRANNE_B200_ABI_VERSION 1
+#define GRANNE_B200_ABI_VERSION 2 /* 2: GRANNE_B200_STAT_FLAGS reports the answering pass; device-resident containers; multi handle */
 
 /* status codes */
 #define GRANNE_B200_OK 0

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol(lib):
     raw = ctypes.CDLL(granne_b200.library_path())
     for n in sorted(names):
         assert hasattr(raw, n), n
-    assert lib.granne_b200_abi_version() == 1
+    assert lib.granne_b200_abi_version() == 2
 
 
 def test_no_torch_or_cxx_types_in_the_header():
