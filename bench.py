@@ -43,6 +43,13 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 METRIC = "QPS @ recall@10>=0.95, angular HNSW search (granne Granne::search), per-box aggregate"
+
+
+def metric_name(a, n):
+    """BASELINE.json's metric, named on the configuration this line was measured on (the same string in both arms)."""
+    et = {"angular": "f32", "angular_int": "i8", "embeddings": "sum-of-embeddings f32"}[a.kind]
+    size = "%dMx%d-d" % (n // 1_000_000, a.dim) if n % 1_000_000 == 0 else "%dx%d-d" % (n, a.dim)
+    return "QPS @ recall@10>=0.95, %s angular %s (granne Granne::search), per-box aggregate" % (size, et)
 UNIT = "queries/s"
 GEN_VERSION = 2          # bump when the synthetic generator changes (part of the cache key)
 CHUNK = 1 << 20          # rows per generation chunk (the generator is seeded per chunk)
@@ -613,7 +620,7 @@ def run_reference(a):
     dt = time.time() - t0
     qps = a.steps * per_step / dt
     prov = shards[0][3]
-    line = {"metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+    line = {"metric": metric_name(a, n), "value": qps, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "i8" if a.kind == "angular_int" else "f32", "data": "synthetic", "impl": "reference",
             "config": workload_config(a, "reference", n, a.gpus, prov),
@@ -1008,7 +1015,7 @@ def main():
         cpu = cpu_baseline(a, index_bytes, cont, q_host, a.cpu_seconds)
     kern = {"angular": "DistF32<%d>" % (a.dim // 32), "angular_int": "DistI8", "embeddings": "DistSum"}[a.kind]
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "metric": metric_name(a, n), "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "i8" if a.kind == "angular_int" else "f32", "data": "synthetic (generated on the GPU)",
         "config": workload_config(a, "ours", n, world, prov),
